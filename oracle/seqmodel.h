@@ -1,0 +1,50 @@
+/*
+ * seqmodel.h — serial CPU statement of the B200 match finder's semantics.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is linked into, imported by or executed
+ * from the product (libqatseqprod.so / the qat-zstd-plugin_b200 package).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, and only
+ * as the checker.
+ *
+ * What it pins: the sm_100a kernels in qat-zstd-plugin_b200/csrc/lz77_kernels.cu are specified
+ * to emit, for every block, exactly the ZSTD_Sequence array this model emits (bit-exact), so a
+ * GPU race or indexing bug shows up as a diff rather than as a slightly different but still
+ * valid parse.  The model is NOT the reference's algorithm (the reference's match finder is
+ * closed QAT hardware, /root/reference/src/qatseqprod.c:1245-1249); the reference-side oracle
+ * is zstd_oracle.c.  The output convention follows QZSTD_decLz4s
+ * (/root/reference/src/qatseqprod.c:1013-1091): matchLength >= 3 for real matches, the last
+ * entry carries the trailing literals with offset = matchLength = 0, rep is left 0.
+ */
+#ifndef B200_SEQMODEL_H
+#define B200_SEQMODEL_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "zstd_abi.h"
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+typedef struct {
+    int longBits;     /* log2 entries of the 8-byte-hash table                      */
+    int shortBits;    /* log2 entries of the short-hash table                       */
+    int shortBytes;   /* bytes hashed by the short hash: 4, 5 or 6                  */
+    int minMatch;     /* shortest match the parser may emit (>= 3)                  */
+    int extCap;       /* per-position extension cap in bytes (multiple of 4)        */
+    int lazyDepth;    /* 0 greedy, 1 lazy, 2 lazy2                                  */
+    int window;       /* pipeline window in positions: lazy look-ahead never crosses a multiple of it */
+} SeqModelParams;
+
+/* Parameters the kernels use for a zstd compression level (1..12). */
+void   seqmodel_params_for_level(int level, SeqModelParams *prm);
+
+/* Parse one block.  Returns the number of entries written (>= 1, last one is the literal
+ * tail), or (size_t)-1 if outCap is too small.  n <= 131072. */
+size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t outCap,
+                      const SeqModelParams *prm);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif
