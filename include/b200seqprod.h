@@ -1,0 +1,110 @@
+/*
+ * b200seqprod.h — C-ABI of the B200 batching layer under libqatseqprod.so.
+ *
+ * Plain C, no CUDA or torch types: pointers, sizes and an opaque engine handle.  This is the
+ * boundary a foreign-language host (cgo / JNI / ctypes) binds; qatseqprod.h (the libzstd-facing
+ * drop-in surface) is implemented on top of it in plain C (csrc/seqprod_host.c).
+ *
+ * What each entry point replaces in the reference (/root/reference/src/qatseqprod.c):
+ *   b200sp_device_count / b200sp_engine_create   icp_sal_userStart + instance discovery
+ *                                                (QZSTD_salUserStart :498-527, QZSTD_getAndShuffleInstance :529-663)
+ *                                                and per-instance buffers (QZSTD_allocInstMem :685-822)
+ *   b200sp_parse_device                          cpaDcCompressData2 submit (:1245-1249) for a whole batch of
+ *                                                blocks already resident in device memory
+ *   b200sp_sync                                  the icp_sal_DcPollInstance loop (:1263-1272)
+ *   b200sp_parse_host                            staging memcpy (:1222-1227) + submit + poll + result fetch
+ *   b200sp_expand                                QZSTD_decLz4s (:1013-1091): device wire format -> ZSTD_Sequence[]
+ *   b200sp_engine_destroy                        QZSTD_cleanUpInstMem / QZSTD_stopQat (:364-426, :306-333)
+ *
+ * Error convention: 0 on success, a negative B200SP_E* code otherwise; b200sp_error_string()
+ * describes the last failure of the calling thread.  Nothing here aborts or exits.
+ */
+#ifndef B200SEQPROD_H
+#define B200SEQPROD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#define B200SP_BLOCK_MAX        (1u << 17)      /* ZSTD_BLOCKSIZE_MAX */
+#define B200SP_SEQ_STRIDE       43696u          /* >= ZSTD_sequenceBound(128 KiB) = 43691, multiple of 8 */
+
+#define B200SP_OK               0
+#define B200SP_ENODEVICE       (-1)   /* no CUDA device / driver */
+#define B200SP_EUNSUPPORTED    (-2)   /* device is not sm_100 or lacks 227 KB shared memory per CTA */
+#define B200SP_EINVAL          (-3)   /* bad argument (alignment, block size, level outside 1..12) */
+#define B200SP_ENOMEM          (-4)
+#define B200SP_ECUDA           (-5)   /* CUDA runtime error, see b200sp_error_string() */
+#define B200SP_ETIMEOUT        (-6)   /* completion not seen within the reference's 2 s budget (:107) */
+
+/* One ZSTD_Sequence as the library's own 16-byte type (identical layout to zstd.h's). */
+typedef struct {
+    uint32_t offset, litLength, matchLength, rep;
+} b200sp_sequence;
+
+typedef struct b200sp_engine b200sp_engine;
+
+/* Number of CUDA devices the driver exposes, whatever their architecture; 0 if there is no
+ * driver or no device ("icp_sal_userStart failed" in the reference's terms). */
+int b200sp_driver_device_count(void);
+
+/* Number of usable (sm_100, enough shared memory) devices; 0 if none; <0 on driver failure. */
+int b200sp_device_count(void);
+
+/* Engine = one device + one stream + scratch buffers.  Not thread-safe: one engine per caller
+ * thread, like one QZSTD state per CCtx (/root/reference/src/qatseqprod.h:139-151). */
+int  b200sp_engine_create(int device, b200sp_engine **engine);
+void b200sp_engine_destroy(b200sp_engine *engine);
+int  b200sp_engine_device(const b200sp_engine *engine);
+int  b200sp_engine_sm_count(const b200sp_engine *engine);
+
+/* Device-resident batch: blocks b = 0..nBlocks-1 start at d_src + b*stride.
+ *   d_sizes == NULL : block b holds min(blockSize, totalSize - b*stride) bytes (a buffer cut into blocks)
+ *   d_sizes != NULL : block b holds d_sizes[b] bytes (device array)
+ * d_src must be 16-byte aligned, stride a multiple of 16, every block <= 128 KiB.
+ * Output: block b's sequences at d_seqs + b*seqStride (seqStride entries >= ZSTD_sequenceBound of
+ * the largest block; B200SP_SEQ_STRIDE always suffices), d_counts[b] = entries written, the last
+ * one being {0, trailing literals, 0}.
+ * Asynchronous on `cudaStream` (a cudaStream_t passed as void*; NULL = the engine's stream). */
+int b200sp_parse_device(b200sp_engine *engine, const void *d_src, uint64_t totalSize,
+                        uint32_t blockSize, uint64_t stride, const uint32_t *d_sizes,
+                        uint32_t nBlocks, int level, b200sp_sequence *d_seqs, uint64_t seqStride,
+                        uint32_t *d_counts, void *cudaStream);
+
+/* Waits for everything queued on the engine's stream. */
+int b200sp_sync(b200sp_engine *engine);
+
+/* Host-resident batch, synchronous: copies h_src to the device (through pinned staging unless
+ * the buffer is already pinned), parses it in blocks of blockSize, and brings back the result in
+ * the 8-byte wire format.  The result arrays are owned by the engine and stay valid until the
+ * next b200sp_parse_host / b200sp_engine_destroy on it. */
+typedef struct {
+    uint32_t nBlocks;
+    const uint32_t *counts;     /* [nBlocks] entries per block, incl. the final literals entry */
+    const uint64_t *offsets;    /* [nBlocks + 1] start of each block's entries in `packed` */
+    const uint64_t *packed;     /* offset | litLength << 17 | matchLength << 35 */
+} b200sp_result;
+
+int b200sp_parse_host(b200sp_engine *engine, const void *h_src, size_t srcSize, uint32_t blockSize,
+                      int level, b200sp_result *result);
+
+/* Wire format -> ZSTD_Sequence[] (rep = 0). */
+void b200sp_expand(const uint64_t *packed, size_t count, b200sp_sequence *out);
+
+/* On-device verification (the analogue of compressAndVerify, :1238): replays every block's
+ * sequences against its input; *d_bad (device, one uint32 per block) gets 0 for a valid block. */
+int b200sp_verify_device(b200sp_engine *engine, const void *d_src, uint64_t totalSize,
+                         uint32_t blockSize, uint64_t stride, const uint32_t *d_sizes,
+                         uint32_t nBlocks, const b200sp_sequence *d_seqs, uint64_t seqStride,
+                         const uint32_t *d_counts, uint32_t *d_bad, void *cudaStream);
+
+const char *b200sp_error_string(void);
+const char *b200sp_version(void);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* B200SEQPROD_H */

@@ -9,8 +9,8 @@
  *   1. candidates  every position p <= n-8 hashes 8 bytes (long) and shortBytes bytes (short)
  *                  and reads-then-overwrites one slot of each table: the candidate is the most
  *                  recent earlier position with the same hash.
- *   2. extension   common prefix of src[p..] and src[cand..], capped at extCap and at n-p; the
- *                  better of the two candidates wins.
+ *   2. extension   common prefix of src[p..] and src[cand..]: candidates are ranked on their first
+ *                  32 bytes, the winner is extended up to extCap (and never past n).
  *   3. propagation B(p) = the match, among all starting at q <= p, that reaches farthest right.
  *   4. parse       greedy left-to-right over B with lazy look-ahead; zero-literal sequences
  *                  repeating the previous offset are merged into their predecessor; the last
@@ -22,6 +22,7 @@
 #include <string.h>
 
 #define MODEL_MAX_BLOCK (1u << 17)
+#define MODEL_PROBE     32u          /* bytes compared per candidate before a winner is picked */
 
 static inline uint32_t rd32(const uint8_t *p)
 {
@@ -108,18 +109,25 @@ size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t o
             tabS[hS] = (uint16_t)(p >> 1);
             uint32_t lim = N - p;
             if (lim > (uint32_t)prm->extCap) lim = (uint32_t)prm->extCap;
-            /* candidate order: long pair (even, odd), then short pair; a later candidate
-             * replaces the best so far if it is longer, or as long and nearer */
+            /* Phase 1: every candidate is measured over its first PROBE bytes only; candidate
+             * order is long pair (even, odd) then short pair; a later candidate replaces the best
+             * so far if it is longer, or as long and nearer.
+             * Phase 2: only the winner is extended, up to extCap. */
+            const uint32_t probe = lim < MODEL_PROBE ? lim : MODEL_PROBE;
             for (int t = 0; t < 2; t++) {
                 for (uint32_t k = 0; k < 2; k++) {
                     const uint32_t q = base[t] + k;
                     if (q >= p) continue;
                     const uint8_t *a = src + p, *b = src + q;
                     uint32_t ml = 0;
-                    while (ml < lim && a[ml] == b[ml]) ml++;
+                    while (ml < probe && a[ml] == b[ml]) ml++;
                     const uint32_t off = p - q;
                     if (ml > bestLen || (ml == bestLen && ml > 0 && off < bestOff)) { bestLen = ml; bestOff = off; }
                 }
+            }
+            if (bestLen == MODEL_PROBE) {
+                const uint8_t *a = src + p, *b = src + p - bestOff;
+                while (bestLen < lim && a[bestLen] == b[bestLen]) bestLen++;
             }
             if (bestLen < (uint32_t)prm->minMatch) bestLen = 0;
         }

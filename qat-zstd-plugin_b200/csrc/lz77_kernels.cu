@@ -1,0 +1,575 @@
+/*
+ * lz77_kernels.cu — sm_100a LZ77 block parser: batch of independent <=128 KiB blocks in HBM ->
+ * ZSTD_Sequence arrays in HBM.
+ *
+ * This is the B200 replacement for the QAT LZ4s engine + QZSTD_decLz4s
+ * (/root/reference/src/qatseqprod.c:1245-1249 submit, :1013-1091 token walk, :1308-1313
+ * incompressible shortcut).  Output convention is the reference's: matchLength >= 3 for real
+ * matches, the last entry is {offset 0, trailing literals, matchLength 0}, `rep` is 0.
+ *
+ * One persistent CTA per SM; a CTA owns one block at a time:
+ *   - the block is staged into shared memory with 1-D TMA bulk copies (UBLKCP), 16 KiB per
+ *     mbarrier so the pipeline starts before the whole block has landed;
+ *   - both hash tables (2 x 16 Ki x u16, positions stored >> 1) live in shared memory;
+ *   - the block flows through a 4-deep ring of 1024-position windows, one role per stage:
+ *       H  hash      16 warps   8-byte + short hash per position, intra-warp duplicate links
+ *       T  table      2 warps   one warp per table walks the window in order: read slot,
+ *                               overwrite with the newer position (exact serial semantics)
+ *       E  extend    16 warps   probe the candidates (4-byte word compares), warp-cooperative
+ *                               long extension, warp prefix-max of match ends
+ *       P  parse      1 warp    lane-parallel speculative greedy/lazy parse (iterated to the
+ *                               serial fixed point), sequence compaction, 16 B stores
+ *     (the H and E roles share the same 16 warps).
+ * The result is bit-identical to oracle/seqmodel.c, which is the serial statement of the same
+ * four steps.  Integer/indexing work only: no tensor cores, no TMEM.
+ */
+#include "lz77_kernels.cuh"
+
+namespace b200sp {
+
+// ------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// Unaligned little-endian 32-bit read from the staged block.
+__device__ __forceinline__ uint32_t ld32u(const uint32_t *in32, uint32_t bytePos)
+{
+    const uint32_t w = bytePos >> 2;
+    return __funnelshift_r(in32[w], in32[w + 1], (bytePos & 3u) * 8u);
+}
+
+__device__ __forceinline__ uint32_t ring_index(uint32_t group, uint32_t lane)
+{
+    return group * 32u + (lane ^ group);   // XOR swizzle: conflict-free by group and by lane
+}
+
+__device__ __forceinline__ int32_t gain_of(uint32_t len, uint32_t off)
+{
+    return static_cast<int32_t>(len * 4u) - static_cast<int32_t>(31 - __clz(off + 1u));
+}
+
+struct Shared {
+    uint32_t *in32;
+    uint16_t *tabL;
+    uint16_t *tabS;
+    uint32_t *ring0;    // [kRing][kWindow]
+    uint32_t *ring1;    // [kRing][kWindow]
+    uint32_t *mask;     // [kRing][kGroups]
+    uint32_t *carry;    // [kGroups + 1][2]
+    uint64_t *mbar;     // [kTmaChunks]
+    volatile int *work; // next block index
+};
+
+// ------------------------------------------------------------------------------------------
+// H: hashes of one 32-position group -> ring words {hash | delta << 16 | last << 21 | valid << 22}
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_hash(const Shared &S, uint32_t slot, uint32_t group, uint32_t lane,
+                                           uint32_t p, uint32_t nh, uint32_t shortMask)
+{
+    const bool valid = p < nh;
+    uint32_t hL = 0, hS = 0;
+    if (valid) {
+        const uint32_t w = p >> 2, sh = (p & 3u) * 8u;
+        const uint32_t w0 = S.in32[w], w1 = S.in32[w + 1], w2 = S.in32[w + 2];
+        const uint32_t lo = __funnelshift_r(w0, w1, sh);
+        const uint32_t hi = __funnelshift_r(w1, w2, sh);
+        hL = (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> (32 - kLongBits);
+        hS = (lo * 0x9E3779B1u + (hi & shortMask) * 0xC2B2AE3Du) >> (32 - kShortBits);
+    }
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const uint32_t geMask = ~((2u << lane) - 1u);      // lanes strictly above
+    // invalid lanes get unique keys so they never link
+    const uint32_t mL = __match_any_sync(0xFFFFFFFFu, valid ? hL : (0x10000u | lane));
+    const uint32_t mS = __match_any_sync(0xFFFFFFFFu, valid ? hS : (0x10000u | lane));
+    const uint32_t bL = mL & ltMask, bS = mS & ltMask;
+    const uint32_t dL = bL ? lane - (31u - __clz(bL)) : 0u;   // distance to the nearest earlier lane with the same hash
+    const uint32_t dS = bS ? lane - (31u - __clz(bS)) : 0u;
+    const uint32_t lastL = (mL & geMask) == 0u, lastS = (mS & geMask) == 0u;
+    const uint32_t idx = slot * kWindow + ring_index(group, lane);
+    S.ring0[idx] = hL | (dL << 16) | (lastL << 21) | (static_cast<uint32_t>(valid) << 22);
+    S.ring1[idx] = hS | (dS << 16) | (lastS << 21) | (static_cast<uint32_t>(valid) << 22);
+}
+
+// ------------------------------------------------------------------------------------------
+// T: one warp walks one table over a window, group by group, in position order.
+// ring word in: hash/links from H; ring word out: candidate (position >> 1) or 0xFFFF.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_table(uint32_t *ring, uint16_t *tab, uint32_t slot, uint32_t lane,
+                                            uint32_t windowBase)
+{
+    uint32_t *r = ring + slot * kWindow;
+#pragma unroll 1
+    for (uint32_t g0 = 0; g0 < kGroups; g0 += 8) {
+        uint32_t w[8], tv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = r[ring_index(g0 + k, lane)];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t h = w[k] & 0xFFFFu;
+            const bool valid = (w[k] >> 22) & 1u;
+            const bool last = (w[k] >> 21) & 1u;
+            const uint32_t p = windowBase + (g0 + k) * 32u + lane;
+            tv[k] = tab[h];
+            if (valid && last) tab[h] = static_cast<uint16_t>(p >> 1);
+            __syncwarp();       // orders this group's stores before the next group's loads
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t delta = (w[k] >> 16) & 31u;
+            const bool valid = (w[k] >> 22) & 1u;
+            const uint32_t p = windowBase + (g0 + k) * 32u + lane;
+            uint32_t cand = delta ? ((p - delta) >> 1) : tv[k];
+            if (!valid) cand = 0xFFFFu;
+            r[ring_index(g0 + k, lane)] = cand;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// E: candidates of one group -> best match per position -> prefix-max of match ends
+// ring out: ring0 = end (p + len, 0 if none so far in this group), ring1 = offset
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t probe_len(const uint32_t *in32, uint32_t p, uint32_t q, uint32_t probe)
+{
+    // caller has already established that the first 4 bytes are equal
+    uint32_t k = 4;
+    while (k < probe) {
+        const uint32_t x = ld32u(in32, p + k) ^ ld32u(in32, q + k);
+        if (x) { k += (__ffs(x) - 1) >> 3; break; }
+        k += 4;
+    }
+    return k < probe ? k : probe;
+}
+
+__device__ __forceinline__ void stage_extend(const Shared &S, uint32_t slot, uint32_t group, uint32_t lane,
+                                             uint32_t p, uint32_t n, uint32_t nh, uint32_t minMatch,
+                                             uint32_t extCap)
+{
+    const uint32_t idx = slot * kWindow + ring_index(group, lane);
+    const uint32_t cL = S.ring0[idx], cS = S.ring1[idx];
+    const uint32_t *in32 = S.in32;
+    uint32_t bestLen = 0, bestOff = 0, lim = 0;
+    if (p < nh) {
+        lim = min(n - p, extCap);
+        const uint32_t probe = min(lim, kProbe);
+        const uint32_t a0 = ld32u(in32, p);
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            const uint32_t c = t ? cS : cL;
+            if (t && cS == cL) break;
+            const uint32_t q0 = 2u * c;
+            if (q0 >= p) continue;                              // also rejects the 0xFFFF empty marker
+            const uint32_t w = q0 >> 2, sh = (q0 & 3u) * 8u;    // q0 is even: sh is 0 or 16
+            const uint32_t x = in32[w], y = in32[w + 1];
+            const uint32_t b0 = __funnelshift_r(x, y, sh);
+            const uint32_t b1 = __funnelshift_r(x, y, sh + 8u);
+            if (b0 == a0) {
+                const uint32_t ml = probe_len(in32, p, q0, probe), off = p - q0;
+                if (ml > bestLen || (ml == bestLen && off < bestOff)) { bestLen = ml; bestOff = off; }
+            }
+            if (q0 + 1 < p && b1 == a0) {
+                const uint32_t ml = probe_len(in32, p, q0 + 1, probe), off = p - q0 - 1;
+                if (ml > bestLen || (ml == bestLen && off < bestOff)) { bestLen = ml; bestOff = off; }
+            }
+        }
+    }
+
+    // Long extension of winners that filled the probe.  A lane continuing its predecessor's
+    // match (same offset, both filled the probe) derives its length from the run head; heads are
+    // extended by the whole warp, 128 bytes per step, far enough to serve all their followers.
+    const bool job = (bestLen == kProbe) && (lim > kProbe);
+    const uint32_t prevOff = __shfl_up_sync(0xFFFFFFFFu, bestOff, 1);
+    const uint32_t jobs = __ballot_sync(0xFFFFFFFFu, job);
+    const bool follower = job && lane > 0 && ((jobs >> (lane - 1)) & 1u) && prevOff == bestOff;
+    uint32_t heads = jobs & ~__ballot_sync(0xFFFFFFFFu, follower);
+    const uint32_t myHead = job ? 31u - __clz(heads & ((2u << lane) - 1u)) : 32u;
+    while (heads) {
+        const uint32_t h = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const uint32_t ph = p - lane + h;                               // head position (uniform)
+        const uint32_t offh = __shfl_sync(0xFFFFFFFFu, bestOff, h);
+        const uint32_t qh = ph - offh;
+        const uint32_t reach = min(n - ph, extCap + 32u);               // how far any follower may need
+        uint32_t U = reach;
+#pragma unroll 1
+        for (uint32_t k0 = kProbe; k0 < reach; k0 += 128u) {
+            const uint32_t k = k0 + lane * 4u;
+            uint32_t x = 0;
+            if (k < reach) x = ld32u(in32, ph + k) ^ ld32u(in32, qh + k);
+            const uint32_t bad = __ballot_sync(0xFFFFFFFFu, x != 0u);
+            if (bad) {
+                const uint32_t l = __ffs(bad) - 1;
+                const uint32_t xl = __shfl_sync(0xFFFFFFFFu, x, l);
+                U = min(reach, k0 + l * 4u + ((__ffs(xl) - 1) >> 3));
+                break;
+            }
+        }
+        if (myHead == h) bestLen = min(lim, U - (lane - h));
+    }
+    if (bestLen < minMatch) bestLen = 0;
+
+    // inclusive prefix-max over the group; strictly greater replaces, ties keep the older match
+    uint32_t end = bestLen ? p + bestLen : 0u, off = bestOff;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t oe = __shfl_up_sync(0xFFFFFFFFu, end, d);
+        const uint32_t oo = __shfl_up_sync(0xFFFFFFFFu, off, d);
+        if (lane >= static_cast<uint32_t>(d) && !(end > oe)) { end = oe; off = oo; }
+    }
+    S.ring0[idx] = end;
+    S.ring1[idx] = off;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, end >= p + minMatch);
+    if (lane == 0) S.mask[slot * kGroups + group] = m;
+}
+
+// ------------------------------------------------------------------------------------------
+// P: parse one window.  Lane j owns positions [base + 32 j, base + 32 j + 32).
+// ------------------------------------------------------------------------------------------
+struct ParseCarry {          // uniform across the warp, carried from window to window
+    uint32_t cursor;         // first position the parser has not consumed yet
+    uint32_t anchor;         // end of the last emitted match
+    uint32_t prevOff;        // offset of the last emitted match
+    uint32_t nOut;           // sequences written so far
+    uint32_t runEnd, runOff; // farthest-reaching match seen so far (propagated B)
+};
+
+struct LaneWalk {
+    uint32_t exit;           // cursor after the lane's segment
+    uint32_t cnt;            // matches taken
+    uint32_t merges;         // matches merged into their in-lane predecessor
+    uint32_t firstPos, firstOff;
+    uint32_t lastEnd, lastOff;
+};
+
+__device__ __forceinline__ void best_at(const Shared &S, uint32_t slot, uint32_t q, uint32_t &e, uint32_t &o)
+{
+    const uint32_t g = (q >> 5) & (kGroups - 1), l = q & 31u;
+    const uint32_t idx = slot * kWindow + ring_index(g, l);
+    e = S.ring0[idx];
+    o = S.ring1[idx];
+    const uint32_t ce = S.carry[2 * g], co = S.carry[2 * g + 1];
+    if (!(e > ce)) { e = ce; o = co; }
+}
+
+// Walks the lane's segment from `entry`.  When `out` is non-null the matches are also emitted:
+// new sequences go to out[idx...], a leading continuation of the previous sequence is returned in
+// `headAdd` (to be added to out[firstIdx - 1].matchLength by the caller).
+template <bool kEmit>
+__device__ __forceinline__ void lane_walk(const Shared &S, uint32_t slot, uint32_t segStart, uint32_t mask,
+                                          uint32_t entry, uint32_t minMatch, uint32_t lazyDepth,
+                                          LaneWalk &r, uint32_t anchor, uint32_t prevOff,
+                                          uint4 *out, uint32_t outIdx, uint32_t &headAdd)
+{
+    uint32_t c = entry;
+    r.cnt = 0; r.merges = 0; r.firstPos = 0; r.firstOff = 0; r.lastEnd = 0; r.lastOff = 0;
+    uint32_t openOff = 0, openLit = 0, openLen = 0;   // sequence being accumulated (emit mode)
+    bool haveOpen = false;
+    headAdd = 0;
+    const uint32_t segEnd = segStart + 32u;
+    while (c < segEnd) {
+        const uint32_t m = mask & (0xFFFFFFFFu << (c - segStart));
+        if (!m) { c = segEnd; break; }
+        uint32_t p = segStart + __ffs(m) - 1;
+        uint32_t e, o;
+        best_at(S, slot, p, e, o);
+        if (lazyDepth >= 1) {
+            for (;;) {
+                const int32_t g0 = gain_of(e - p, o);
+                uint32_t q = p + 1, e1, o1;
+                if ((q & (kWindow - 1)) == 0) break;
+                best_at(S, slot, q, e1, o1);
+                if (e1 < q + minMatch) break;
+                if (gain_of(e1 - q, o1) > g0 + 4) { p = q; e = e1; o = o1; continue; }
+                if (lazyDepth < 2) break;
+                q = p + 2;
+                if ((q & (kWindow - 1)) == 0) break;
+                best_at(S, slot, q, e1, o1);
+                if (e1 < q + minMatch) break;
+                if (gain_of(e1 - q, o1) > g0 + 7) { p = q; e = e1; o = o1; continue; }
+                break;
+            }
+        }
+        // take the match [p, e) at offset o
+        if (r.cnt == 0) { r.firstPos = p; r.firstOff = o; }
+        else if (p == r.lastEnd && o == r.lastOff) r.merges++;
+        r.cnt++;
+        if (kEmit) {
+            const uint32_t lit = p - anchor, len = e - p;
+            if (lit == 0 && o == prevOff && anchor > 0) {
+                if (haveOpen) openLen += len; else headAdd += len;
+            } else {
+                if (haveOpen) out[outIdx++] = make_uint4(openOff, openLit, openLen, 0u);
+                openOff = o; openLit = lit; openLen = len; haveOpen = true;
+            }
+            anchor = e; prevOff = o;
+        }
+        r.lastEnd = e; r.lastOff = o;
+        c = e;
+    }
+    if (kEmit && haveOpen) out[outIdx] = make_uint4(openOff, openLit, openLen, 0u);
+    r.exit = c;
+}
+
+__device__ __forceinline__ void stage_parse(const Shared &S, uint32_t slot, uint32_t lane, uint32_t base,
+                                            uint32_t minMatch, uint32_t lazyDepth, ParseCarry &pc, uint4 *out)
+{
+    const uint32_t segStart = base + lane * 32u;
+    // ---- carry of the propagated best match into every group
+    const uint32_t i31 = slot * kWindow + ring_index(lane, 31u);
+    uint32_t incE = S.ring0[i31], incO = S.ring1[i31];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t oe = __shfl_up_sync(0xFFFFFFFFu, incE, d);
+        const uint32_t oo = __shfl_up_sync(0xFFFFFFFFu, incO, d);
+        if (lane >= static_cast<uint32_t>(d) && !(incE > oe)) { incE = oe; incO = oo; }
+    }
+    uint32_t exE = __shfl_up_sync(0xFFFFFFFFu, incE, 1), exO = __shfl_up_sync(0xFFFFFFFFu, incO, 1);
+    if (lane == 0 || !(exE > pc.runEnd)) { exE = pc.runEnd; exO = pc.runOff; }
+    S.carry[2 * lane] = exE;
+    S.carry[2 * lane + 1] = exO;
+    {
+        uint32_t tE = __shfl_sync(0xFFFFFFFFu, incE, 31), tO = __shfl_sync(0xFFFFFFFFu, incO, 31);
+        if (tE > pc.runEnd) { pc.runEnd = tE; pc.runOff = tO; }
+    }
+    __syncwarp();
+
+    // ---- positions of this segment that have a usable match
+    uint32_t mask = S.mask[slot * kGroups + lane];
+    if (exE >= segStart + minMatch) {
+        const uint32_t cnt = exE - minMatch - segStart + 1u;
+        mask |= cnt >= 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
+    }
+
+    // ---- speculative parse, iterated until every lane's entry equals its predecessor's exit
+    LaneWalk w;
+    uint32_t dummy;
+    uint32_t entry = lane == 0 ? max(pc.cursor, base) : segStart;
+    lane_walk<false>(S, slot, segStart, mask, entry, minMatch, lazyDepth, w, 0, 0, nullptr, 0, dummy);
+    for (;;) {
+        const uint32_t prevExit = __shfl_up_sync(0xFFFFFFFFu, w.exit, 1);
+        const uint32_t want = lane == 0 ? entry : max(prevExit, segStart);
+        const bool changed = want != entry;
+        if (!__any_sync(0xFFFFFFFFu, changed)) break;
+        if (changed) {
+            entry = want;
+            lane_walk<false>(S, slot, segStart, mask, entry, minMatch, lazyDepth, w, 0, 0, nullptr, 0, dummy);
+        }
+    }
+
+    // ---- anchor / previous offset at each lane's entry: exclusive "last match" scan
+    uint32_t aE = w.cnt ? w.lastEnd : 0u, aO = w.lastOff;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t oe = __shfl_up_sync(0xFFFFFFFFu, aE, d);
+        const uint32_t oo = __shfl_up_sync(0xFFFFFFFFu, aO, d);
+        if (lane >= static_cast<uint32_t>(d) && !(aE > oe)) { aE = oe; aO = oo; }
+    }
+    const uint32_t totE = __shfl_sync(0xFFFFFFFFu, aE, 31), totO = __shfl_sync(0xFFFFFFFFu, aO, 31);
+    uint32_t anchor = __shfl_up_sync(0xFFFFFFFFu, aE, 1), prevOff = __shfl_up_sync(0xFFFFFFFFu, aO, 1);
+    if (lane == 0 || anchor == 0) { anchor = pc.anchor; prevOff = pc.prevOff; }
+
+    // ---- output slots
+    const bool headMerge = w.cnt && w.firstPos == anchor && w.firstOff == prevOff && anchor > 0;
+    const uint32_t fresh = w.cnt - w.merges - (headMerge ? 1u : 0u);
+    uint32_t incl = fresh;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= static_cast<uint32_t>(d)) incl += v;
+    }
+    const uint32_t firstIdx = pc.nOut + incl - fresh;
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+
+    uint32_t headAdd = 0;
+    if (w.cnt) {
+        LaneWalk w2;
+        lane_walk<true>(S, slot, segStart, mask, entry, minMatch, lazyDepth, w2, anchor, prevOff, out, firstIdx, headAdd);
+    }
+    __syncwarp();
+    if (headAdd) atomicAdd(&out[firstIdx - 1].z, headAdd);   // continuation of an earlier lane's sequence
+    __syncwarp();
+
+    pc.cursor = __shfl_sync(0xFFFFFFFFu, w.exit, 31);
+    if (totE) { pc.anchor = totE; pc.prevOff = totO; }
+    pc.nOut += total;
+}
+
+// ------------------------------------------------------------------------------------------
+// the persistent kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParseParams P)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    Shared S;
+    {
+        uint8_t *p = smem;
+        S.in32 = reinterpret_cast<uint32_t *>(p);  p += kSmemInput;
+        S.tabL = reinterpret_cast<uint16_t *>(p);  p += kSmemTabL;
+        S.tabS = reinterpret_cast<uint16_t *>(p);  p += kSmemTabS;
+        S.ring0 = reinterpret_cast<uint32_t *>(p); p += kSmemRing / 2;
+        S.ring1 = reinterpret_cast<uint32_t *>(p); p += kSmemRing / 2;
+        S.mask = reinterpret_cast<uint32_t *>(p);  p += kSmemMask;
+        S.carry = reinterpret_cast<uint32_t *>(p); p += kSmemCarry;
+        S.mbar = reinterpret_cast<uint64_t *>(p);  p += kTmaChunks * 8;
+        S.work = reinterpret_cast<volatile int *>(p);
+    }
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (uint32_t c = 0; c < kTmaChunks; c++) mbar_init(smem_u32(&S.mbar[c]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t tmaParity = 0;            // bit c = phase parity mbarrier c completes next
+
+    for (;;) {
+        __syncthreads();                       // previous block fully retired; mbarriers initialised
+        if (tid == 0) *S.work = static_cast<int>(atomicAdd(P.workCounter, 1u));
+        __syncthreads();
+        const uint32_t b = static_cast<uint32_t>(*S.work);
+        if (b >= P.nBlocks) break;
+
+        uint32_t n;
+        if (P.sizes) n = P.sizes[b];
+        else {
+            const uint64_t start = static_cast<uint64_t>(b) * P.stride;
+            const uint64_t left = P.totalSize > start ? P.totalSize - start : 0;
+            n = left < P.blockSize ? static_cast<uint32_t>(left) : P.blockSize;
+        }
+        if (n > kBlockMax) n = kBlockMax;
+        const uint8_t *gsrc = P.src + static_cast<uint64_t>(b) * P.stride;
+        uint4 *out = P.seqs + static_cast<uint64_t>(b) * P.seqStride;
+        const uint32_t bulk = n & ~15u;
+        const uint32_t nChunks = (bulk + kTmaChunk - 1) / kTmaChunk;
+
+        // ---- stage the block: TMA bulk copies (one elected thread) + ragged tail + table reset
+        if (tid == 0) {
+            fence_proxy_async();               // earlier generic-proxy reads of the buffer are done
+            for (uint32_t c = 0; c < nChunks; c++) {
+                const uint32_t bytes = min(kTmaChunk, bulk - c * kTmaChunk);
+                const uint32_t bar = smem_u32(&S.mbar[c]);
+                mbar_expect_tx(bar, bytes);
+                tma_load_1d(smem_u32(S.in32) + c * kTmaChunk, gsrc + c * kTmaChunk, bytes, bar);
+            }
+        }
+        if (tid >= 32 && tid < 32 + (n - bulk))
+            reinterpret_cast<uint8_t *>(S.in32)[bulk + tid - 32] = gsrc[bulk + tid - 32];
+        {
+            uint4 *t = reinterpret_cast<uint4 *>(S.tabL);    // tabL and tabS are contiguous
+            const uint4 ff = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            for (uint32_t i = tid; i < (kSmemTabL + kSmemTabS) / 16; i += kThreads) t[i] = ff;
+        }
+        __syncthreads();
+
+        const uint32_t nh = n >= 8 ? n - 7 : 0;
+        const uint32_t nW = (n + kWindow - 1) / kWindow;
+        uint32_t chunksSeen = 0;
+        ParseCarry pc = {0, 0, 0, 0, 0, 0};
+
+        for (uint32_t t = 0; t < nW + 3; t++) {
+            if (warp < kEhWarps) {
+                // bytes this stage may touch: hashing window t reads < (t+1)*1024 + 11, extending
+                // window t-2 reads < (t-1)*1024 + extCap + 36 + 3
+                const uint32_t need = min(bulk, (t + 1) * kWindow + 16u);
+                const uint32_t wantChunks = (need + kTmaChunk - 1) / kTmaChunk;
+                while (chunksSeen < wantChunks) { mbar_wait(smem_u32(&S.mbar[chunksSeen]), (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
+                if (t >= 2 && t - 2 < nW) {
+                    const uint32_t wdx = t - 2, slot = wdx & (kRing - 1);
+                    for (uint32_t g = warp; g < kGroups; g += kEhWarps)
+                        stage_extend(S, slot, g, lane, wdx * kWindow + g * 32u + lane, n, nh, P.minMatch, P.extCap);
+                }
+                if (t < nW) {
+                    const uint32_t slot = t & (kRing - 1);
+                    for (uint32_t g = warp; g < kGroups; g += kEhWarps)
+                        stage_hash(S, slot, g, lane, t * kWindow + g * 32u + lane, nh, P.shortMask);
+                }
+            } else if (warp == kWarpTabL) {
+                if (t >= 1 && t - 1 < nW) stage_table(S.ring0, S.tabL, (t - 1) & (kRing - 1), lane, (t - 1) * kWindow);
+            } else if (warp == kWarpTabS) {
+                if (t >= 1 && t - 1 < nW) stage_table(S.ring1, S.tabS, (t - 1) & (kRing - 1), lane, (t - 1) * kWindow);
+            } else {
+                if (t >= 3) stage_parse(S, (t - 3) & (kRing - 1), lane, (t - 3) * kWindow, P.minMatch, P.lazyDepth, pc, out);
+            }
+            __syncthreads();
+        }
+
+        if (warp == kWarpParse && lane == 0) {
+            out[pc.nOut] = make_uint4(0u, n - pc.anchor, 0u, 0u);   // trailing literals / block delimiter
+            P.counts[b] = pc.nOut + 1u;
+        }
+        // every issued chunk must have landed before its mbarrier is re-armed for the next block
+        if (warp == 0) while (chunksSeen < nChunks) { mbar_wait(smem_u32(&S.mbar[chunksSeen]), (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
+        tmaParity ^= (1u << nChunks) - 1u;   // only the barriers armed for this block changed phase
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+bool params_for_level(int level, ParseParams &p)
+{
+    if (level < 1 || level > 12) return false;
+    p.minMatch = 4;
+    p.extCap = kMaxExtCap;
+    if (level <= 2)      { p.shortMask = 0xFFFFu; p.lazyDepth = 0; }   // fast class
+    else if (level <= 4) { p.shortMask = 0xFFu;   p.lazyDepth = 1; }   // dfast class
+    else                 { p.shortMask = 0u;      p.lazyDepth = 2; }   // greedy/lazy/btlazy2 classes
+    return true;
+}
+
+cudaError_t configure_kernels()
+{
+    return cudaFuncSetAttribute(lz77_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kSmemTotal));
+}
+
+cudaError_t launch_parse(const ParseParams &p, int numSMs, cudaStream_t stream)
+{
+    if (p.nBlocks == 0) return cudaSuccess;
+    const unsigned grid = static_cast<unsigned>(p.nBlocks < static_cast<uint32_t>(numSMs) ? p.nBlocks : numSMs);
+    lz77_parse_kernel<<<grid, kThreads, kSmemTotal, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace b200sp

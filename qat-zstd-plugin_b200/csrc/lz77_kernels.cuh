@@ -1,0 +1,72 @@
+/*
+ * lz77_kernels.cuh — launch interface of the sm_100a LZ77 block parser (internal to the library;
+ * the public C-ABI is include/b200seqprod.h).
+ *
+ * Replaces the QAT LZ4s engine behind cpaDcCompressData2 plus the QZSTD_decLz4s token walk
+ * (/root/reference/src/qatseqprod.c:1245-1249, :1013-1091): one launch parses a batch of
+ * independent blocks (<= 128 KiB each) resident in HBM into ZSTD_Sequence arrays in HBM.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200sp {
+
+constexpr uint32_t kBlockMax      = 1u << 17;   // ZSTD_BLOCKSIZE_MAX
+constexpr uint32_t kWindow        = 1024;       // positions per pipeline window
+constexpr uint32_t kGroups        = kWindow / 32;
+constexpr uint32_t kRing          = 4;          // windows in flight: hash, table, extend, parse
+constexpr uint32_t kLongBits      = 14;
+constexpr uint32_t kShortBits     = 14;
+constexpr uint32_t kProbe         = 32;         // bytes compared per candidate before a winner is picked
+constexpr uint32_t kMaxExtCap     = 256;
+constexpr uint32_t kInputPad      = 320;        // readable slack after the block in shared memory
+constexpr uint32_t kTmaChunk      = 16384;
+constexpr uint32_t kTmaChunks     = kBlockMax / kTmaChunk;
+
+constexpr int kEhWarps   = 16;                  // hash + extension warps
+constexpr int kWarpTabL  = kEhWarps;            // serial owner of the long-hash table
+constexpr int kWarpTabS  = kEhWarps + 1;        // serial owner of the short-hash table
+constexpr int kWarpParse = kEhWarps + 2;        // speculative lane-parallel parser + emitter
+constexpr int kNumWarps  = kEhWarps + 3;
+constexpr int kThreads   = kNumWarps * 32;
+
+// Shared-memory carve-up (bytes)
+constexpr uint32_t kSmemInput   = kBlockMax + kInputPad;
+constexpr uint32_t kSmemTabL    = (1u << kLongBits) * 2;
+constexpr uint32_t kSmemTabS    = (1u << kShortBits) * 2;
+constexpr uint32_t kSmemRing    = kRing * 2 * kWindow * 4;
+constexpr uint32_t kSmemMask    = kRing * kGroups * 4;
+constexpr uint32_t kSmemCarry   = (kGroups + 1) * 2 * 4;
+constexpr uint32_t kSmemMisc    = 128;          // mbarriers + work-item slot
+constexpr uint32_t kSmemTotal   = kSmemInput + kSmemTabL + kSmemTabS + kSmemRing + kSmemMask + kSmemCarry + kSmemMisc;
+static_assert(kSmemTotal <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+struct ParseParams {
+    const uint8_t *src;        // batch base, 16-byte aligned
+    uint64_t stride;           // byte distance between consecutive blocks (multiple of 16)
+    uint64_t totalSize;        // only used when sizes == nullptr: block b holds min(blockSize, totalSize - b*stride)
+    uint32_t blockSize;        // nominal block size (<= 128 KiB) when sizes == nullptr
+    const uint32_t *sizes;     // optional per-block sizes (device), each <= 128 KiB
+    uint32_t nBlocks;
+    uint4 *seqs;               // ZSTD_Sequence arrays, seqStride entries per block
+    uint64_t seqStride;
+    uint32_t *counts;          // entries written per block (incl. the final literals entry)
+    unsigned int *workCounter; // zeroed before launch; dynamic block scheduler
+    uint32_t shortMask;        // mask on bytes 4..7 for the short hash: 0 (4 B), 0xFF (5 B), 0xFFFF (6 B)
+    uint32_t minMatch;         // >= 4
+    uint32_t extCap;           // <= kMaxExtCap
+    uint32_t lazyDepth;        // 0..2
+};
+
+// Fills the per-level fields of ParseParams. Returns false for levels outside 1..12
+// (same range the reference accepts, /root/reference/src/qatseqprod.c:1132-1137).
+bool params_for_level(int level, ParseParams &p);
+
+// Launches the persistent parser (grid = number of SMs) on `stream`.
+cudaError_t launch_parse(const ParseParams &p, int numSMs, cudaStream_t stream);
+
+// One-time per-device setup (opt-in shared memory). Returns cudaSuccess or the CUDA error.
+cudaError_t configure_kernels();
+
+}  // namespace b200sp

@@ -1,0 +1,240 @@
+/*
+ * seqprod_host.c — the libzstd-facing plugin layer of libqatseqprod.so, plain C.
+ *
+ * Mirrors the public behaviour of /root/reference/src/qatseqprod.c on top of the C-ABI batching
+ * layer (include/b200seqprod.h); it never includes a CUDA header.
+ *
+ *   reference                                        here
+ *   gProcess + mutex (:180-183)                      g_process + mutex
+ *   QZSTD_startQatDevice (:948-964)                  same FAIL -> STARTED -> OK state machine
+ *   QZSTD_stopQatDevice (:428-449)                   back to FAIL (engines are owned by states)
+ *   QZSTD_createSeqProdState/free (:992-1011)        state = engine (stream + buffers), lazily created
+ *   qatSequenceProducer (:1106-1336)                 same argument checks in the same order (:1123-1137),
+ *                                                    same device-down policy (:1140-1152, retry every
+ *                                                    1000th block), same result check rc >= cap-1 (:1318)
+ *   QZSTD_grabInstance (:905-928)                    one engine per state: no contention, no grab
+ *   QZSTD_decLz4s (:1013-1091)                       b200sp_expand: 8-byte wire format -> ZSTD_Sequence
+ */
+#include "qatseqprod.h"
+#include "b200seqprod.h"
+
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define KB                            (1024)
+#define COMP_LVL_MINIMUM              (1)
+#define COMP_LVL_MAXIMUM              (12)
+#define NUM_BLOCK_OF_RETRY_INTERVAL   (1000)     /* /root/reference/src/qatseqprod.c:88 */
+
+typedef struct {
+    int status;                 /* QZSTD_FAIL / QZSTD_STARTED / QZSTD_OK */
+    pthread_mutex_t mutex;
+} QZSTD_Process_T;
+
+static QZSTD_Process_T g_process = { QZSTD_FAIL, PTHREAD_MUTEX_INITIALIZER };
+
+typedef struct {
+    b200sp_engine *engine;          /* lazily created on the first offloaded block */
+    unsigned int failOffloadCnt;    /* blocks refused while the device is down (:1141) */
+    /* look-ahead */
+    const unsigned char *hintSrc;
+    size_t hintSize, hintBlock;
+    int batchLevel;                 /* level the cached batch was parsed at, 0 = no batch */
+    b200sp_result batch;
+    /* counters */
+    unsigned long long calls, errors, batched;
+} QZSTD_State_T;
+
+/* ---- logging: same levels as the reference's QZSTD_LOG (:187-205), runtime switch ---------- */
+static int log_level(void)
+{
+    static int level = -1;
+    if (level < 0) {
+        const char *e = getenv("QZSTD_DEBUGLEVEL");
+        level = e ? atoi(e) : 0;
+    }
+    return level;
+}
+#define QZSTD_LOG(l, ...) do { if (log_level() >= (l)) fprintf(stderr, __VA_ARGS__); } while (0)
+
+static int force_error(void)
+{
+    /* fault injection: makes every producer call fail so the application's software fallback
+     * (ZSTD_c_enableSeqProducerFallback) can be exercised on a healthy device */
+    const char *e = getenv("QZSTD_FORCE_ERROR");
+    return e && *e && *e != '0';
+}
+
+const char *QZSTD_version(void)
+{
+    return QZSTD_VERSION;
+}
+
+int QZSTD_startQatDevice(void)
+{
+    int status;
+    pthread_mutex_lock(&g_process.mutex);
+    if (QZSTD_FAIL == g_process.status) {
+        /* driver up?  (icp_sal_userStart in the reference, :498-527) */
+        int total = b200sp_driver_device_count();
+        g_process.status = total > 0 ? QZSTD_STARTED : QZSTD_FAIL;
+    }
+    if (QZSTD_STARTED == g_process.status) {
+        /* a device with the required capability?  (instance discovery + capability filter, :529-663) */
+        g_process.status = b200sp_device_count() > 0 ? QZSTD_OK : QZSTD_STARTED;
+    }
+    status = g_process.status;
+    QZSTD_LOG(2, "InitStatus: %d\n", status);
+    pthread_mutex_unlock(&g_process.mutex);
+    return status;
+}
+
+void QZSTD_stopQatDevice(void)
+{
+    pthread_mutex_lock(&g_process.mutex);
+    g_process.status = QZSTD_FAIL;
+    pthread_mutex_unlock(&g_process.mutex);
+}
+
+void *QZSTD_createSeqProdState(void)
+{
+    QZSTD_State_T *s = (QZSTD_State_T *)calloc(1, sizeof(QZSTD_State_T));
+    return (void *)s;
+}
+
+void QZSTD_freeSeqProdState(void *sequenceProducerState)
+{
+    QZSTD_State_T *s = (QZSTD_State_T *)sequenceProducerState;
+    if (s) {
+        if (s->engine) {
+            b200sp_engine_destroy(s->engine);
+            s->engine = NULL;
+        }
+        free(s);
+    }
+}
+
+void QZSTD_hintSource(void *sequenceProducerState, const void *src, size_t srcSize, size_t blockSize)
+{
+    QZSTD_State_T *s = (QZSTD_State_T *)sequenceProducerState;
+    if (!s) return;
+    s->hintSrc = (const unsigned char *)src;
+    s->hintSize = src ? srcSize : 0;
+    s->hintBlock = blockSize ? blockSize : ZSTD_BLOCKSIZE_MAX;
+    s->batchLevel = 0;
+}
+
+void QZSTD_getStats(const void *sequenceProducerState, unsigned long long *calls,
+                    unsigned long long *errors, unsigned long long *batched)
+{
+    const QZSTD_State_T *s = (const QZSTD_State_T *)sequenceProducerState;
+    if (calls) *calls = s ? s->calls : 0;
+    if (errors) *errors = s ? s->errors : 0;
+    if (batched) *batched = s ? s->batched : 0;
+}
+
+static size_t producer_error(QZSTD_State_T *s)
+{
+    if (s) s->errors++;
+    return ZSTD_SEQUENCE_PRODUCER_ERROR;
+}
+
+size_t qatSequenceProducer(
+    void *sequenceProducerState, ZSTD_Sequence *outSeqs, size_t outSeqsCapacity,
+    const void *src, size_t srcSize,
+    const void *dict, size_t dictSize,
+    int compressionLevel,
+    size_t windowSize)
+{
+    QZSTD_State_T *s = (QZSTD_State_T *)sequenceProducerState;
+    size_t rc;
+
+    if (s) s->calls++;
+
+    if (windowSize < (srcSize < 32 * KB ? srcSize : 32 * KB) || dictSize > 0 || dict) {
+        QZSTD_LOG(2, "windowSize/dictionary not supported, windowSize: %lu, srcSize: %lu, dictSize: %lu\n",
+                  (unsigned long)windowSize, (unsigned long)srcSize, (unsigned long)dictSize);
+        return producer_error(s);
+    }
+
+    if (compressionLevel < COMP_LVL_MINIMUM || compressionLevel > COMP_LVL_MAXIMUM) {
+        QZSTD_LOG(1, "Only L1-L12 can be offloaded, current compression level: %d\n", compressionLevel);
+        return producer_error(s);
+    }
+
+    if (!s || !outSeqs || !src || srcSize == 0 || srcSize > ZSTD_BLOCKSIZE_MAX || force_error()) {
+        return producer_error(s);
+    }
+
+    /* device status: fail fast, retry the start every 1000th refused block (:1140-1152) */
+    if (g_process.status != QZSTD_OK) {
+        s->failOffloadCnt++;
+        if (s->failOffloadCnt >= NUM_BLOCK_OF_RETRY_INTERVAL) {
+            s->failOffloadCnt = 0;
+            if (QZSTD_startQatDevice() != QZSTD_OK) {
+                QZSTD_LOG(1, "Tried to restart the device, but failed\n");
+                return producer_error(s);
+            }
+        } else {
+            QZSTD_LOG(1, "The device was not successfully started\n");
+            return producer_error(s);
+        }
+    }
+
+    if (!s->engine) {
+        if (b200sp_engine_create(0, &s->engine) != B200SP_OK) {
+            QZSTD_LOG(1, "Failed to create engine: %s\n", b200sp_error_string());
+            return producer_error(s);
+        }
+    }
+
+    /* look-ahead: serve the block from (or first build) the batch over the hinted buffer */
+    {
+        const unsigned char *p = (const unsigned char *)src;
+        if (s->hintSrc && p >= s->hintSrc && p + srcSize <= s->hintSrc + s->hintSize &&
+            (size_t)(p - s->hintSrc) % s->hintBlock == 0) {
+            const size_t idx = (size_t)(p - s->hintSrc) / s->hintBlock;
+            const size_t left = s->hintSize - idx * s->hintBlock;
+            const size_t expect = left < s->hintBlock ? left : s->hintBlock;
+            if (expect == srcSize) {
+                if (s->batchLevel != compressionLevel) {
+                    if (b200sp_parse_host(s->engine, s->hintSrc, s->hintSize, (uint32_t)s->hintBlock,
+                                          compressionLevel, &s->batch) != B200SP_OK) {
+                        QZSTD_LOG(1, "Batch parse failed: %s\n", b200sp_error_string());
+                        s->batchLevel = 0;
+                        return producer_error(s);
+                    }
+                    s->batchLevel = compressionLevel;
+                }
+                if (idx < s->batch.nBlocks) {
+                    rc = s->batch.counts[idx];
+                    if (rc >= outSeqsCapacity - 1) return producer_error(s);
+                    b200sp_expand(s->batch.packed + s->batch.offsets[idx], rc, (b200sp_sequence *)outSeqs);
+                    s->batched++;
+                    return rc;
+                }
+            }
+        }
+    }
+
+    /* batch of one block */
+    {
+        b200sp_result one;
+        if (b200sp_parse_host(s->engine, src, srcSize, (uint32_t)srcSize, compressionLevel, &one) != B200SP_OK ||
+            one.nBlocks != 1) {
+            QZSTD_LOG(1, "Parse failed: %s\n", b200sp_error_string());
+            return producer_error(s);
+        }
+        s->batchLevel = 0;          /* the engine's result buffers were reused */
+        rc = one.counts[0];
+        if (rc >= outSeqsCapacity - 1) {        /* same guard as the reference (:1318-1322) */
+            QZSTD_LOG(1, "Sequence count exceeds capacity\n");
+            return producer_error(s);
+        }
+        b200sp_expand(one.packed, rc, (b200sp_sequence *)outSeqs);
+    }
+    QZSTD_LOG(2, "Produced %lu sequences\n", (unsigned long)rc);
+    return rc;
+}

@@ -1,0 +1,155 @@
+"""-m gpu: the CUDA path through the C-ABI against the oracle.
+
+Parity bars (integer work, so all exact):
+  * every block's ZSTD_Sequence array is bit-identical to the serial model (oracle/seqmodel.c);
+  * the sequences replay to exactly the input (oracle validator and the on-device verifier);
+  * ZSTD_compress2 with qatSequenceProducer registered round-trips through stock libzstd
+    (the reference's own and only test, /root/reference/test/test.c:102-136), with zero producer errors;
+  * compressed size within +-1 % of chunked stock libzstd at the same level on the mixed corpus.
+"""
+import numpy as np
+import pytest
+
+from tests import datagen
+from tests.gpu_util import check_against_model, parse_on_gpu
+
+pytestmark = pytest.mark.gpu
+BLOCK = 1 << 17
+
+
+@pytest.mark.parametrize("maker,seed", [
+    (datagen.text_like, 11), (datagen.records, 12), (datagen.binary_like, 13), (datagen.rand_bytes, 14),
+])
+def test_model_parity_by_data_kind(pkg, oracle, engine, maker, seed):
+    data = maker(3 * BLOCK + 777, seed)
+    assert check_against_model(pkg, oracle, engine, data) >= 4
+
+
+def test_model_parity_zero_and_periodic(pkg, oracle, engine):
+    for data in (datagen.zeros(2 * BLOCK), datagen.periodic(BLOCK + 5000, 1), datagen.periodic(2 * BLOCK, 3),
+                 datagen.periodic(BLOCK, 100), datagen.periodic(BLOCK, 70000), b"ab" * 40000):
+        check_against_model(pkg, oracle, engine, data)
+
+
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 9, 12])
+def test_model_parity_all_level_classes(pkg, oracle, engine, level):
+    data = datagen.mixed_corpus(5 * BLOCK + 4321, seed=20 + level)
+    check_against_model(pkg, oracle, engine, data, level=level)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 100, 255, 256, 257, 1023, 1024, 1025,
+                               2047, 2048, 4095, 4096, 5000, 16383, 16384, 16385, 65535, 65536, 65537, 131071, 131072])
+def test_ragged_sizes(pkg, oracle, engine, n):
+    """Empty, tiny and ragged single blocks, incl. the 16-byte TMA granule and 16 KiB chunk edges."""
+    data = datagen.text_like(max(n, 1), seed=n)[:n]
+    counts, seqs, bad = parse_on_gpu(pkg, engine, data)
+    if n == 0:
+        assert counts.shape[0] == 0
+        return
+    got = seqs[0, :counts[0]]
+    want = oracle.model_block(data, 3)
+    assert bad[0] == 0 and oracle.validate(data, got) == 0
+    assert got.shape == want.shape and (got == want).all()
+    assert got[-1, 0] == 0 and got[-1, 2] == 0          # last entry = trailing literals (reference convention)
+
+
+def test_small_block_sizes_and_strides(pkg, oracle, engine):
+    """blockSize < 128 KiB (the reference benchmark's -c 32K/64K chunks) and explicit per-block sizes."""
+    data = datagen.mixed_corpus(700000, seed=31)
+    for bs in (4096, 32768, 65536):
+        check_against_model(pkg, oracle, engine, data[:10 * bs + 99], block_size=bs)
+    sizes = [131072, 5, 70000, 0, 131072, 16, 9999]
+    stride = 131072
+    buf = bytearray(stride * len(sizes))
+    rng = np.random.default_rng(5)
+    for i, s in enumerate(sizes):
+        buf[i * stride:i * stride + s] = datagen.records(s, seed=int(rng.integers(1 << 30)))[:s]
+    counts, seqs, bad = parse_on_gpu(pkg, engine, bytes(buf), sizes=sizes, stride=stride)
+    for i, s in enumerate(sizes):
+        blk = bytes(buf[i * stride:i * stride + s])
+        got = seqs[i, :counts[i]]
+        want = oracle.model_block(blk, 3)
+        assert bad[i] == 0
+        assert got.shape == want.shape and (got == want).all(), f"sized block {i}"
+
+
+def test_incompressible_block_is_one_literal_run(pkg, engine):
+    """Config #5 / the reference's dataUncompressed shortcut (/root/reference/src/qatseqprod.c:1308-1313):
+    a uniform-random block comes back as exactly one entry {0, srcSize, 0}."""
+    data = datagen.rand_bytes(4 * BLOCK, seed=99)
+    counts, seqs, bad = parse_on_gpu(pkg, engine, data)
+    assert (bad == 0).all()
+    for b in range(4):
+        assert counts[b] == 1 and tuple(seqs[b, 0, :3]) == (0, BLOCK, 0)
+
+
+def test_determinism_and_many_blocks(pkg, oracle, engine):
+    """More blocks than SMs (dynamic scheduler, table reset between blocks): two runs are identical and
+    a checksum over every block matches the model on a sample of blocks."""
+    data = datagen.mixed_corpus(400 * BLOCK, seed=41)
+    c1, s1, bad1 = parse_on_gpu(pkg, engine, data)
+    c2, s2, _ = parse_on_gpu(pkg, engine, data)
+    assert (bad1 == 0).all()
+    assert (c1 == c2).all()
+    for b in range(0, 400, 1):
+        assert (s1[b, :c1[b]] == s2[b, :c2[b]]).all()
+    for b in range(0, 400, 37):
+        blk = data[b * BLOCK:(b + 1) * BLOCK]
+        want = oracle.model_block(blk, 3)
+        got = s1[b, :c1[b]]
+        assert got.shape == want.shape and (got == want).all(), f"block {b}"
+
+
+def test_round_trip_through_libzstd_and_ratio(pkg, oracle):
+    """The reference's test.c flow with the real plugin entry points, plus the +-1 % ratio bar."""
+    data = datagen.mixed_corpus(48 * BLOCK + 1000, seed=51)
+    q = pkg.QatSeqProd
+    assert q.startQatDevice() == pkg.QZSTD_OK
+    st = q.createSeqProdState()
+    try:
+        for level in (1, 3, 6):
+            ref = oracle.chunked_compress(data, BLOCK, level)
+            r = oracle.compress_with_producer(data, q.producer, st, chunk=BLOCK, level=level, repcodes=1)
+            assert r["round_trip"] and r["errors"] == 0 and r["calls"] == 49, r
+            delta = r["csize"] / ref - 1
+            print(f"L{level}: csize {r['csize']} vs chunked stock {ref}: {100 * delta:+.2f}%")
+            if level == 3:
+                assert abs(delta) <= 0.01 or delta < 0, f"ratio delta {delta:+.4f} outside the +-1 % bar"
+        # whole buffer as ONE frame: libzstd cuts it into 128 KiB blocks and calls the producer per block
+        r = oracle.compress_with_producer(data, q.producer, st, chunk=len(data), level=3)
+        assert r["round_trip"] and r["errors"] == 0 and r["calls"] == 49
+        # look-ahead hint: one GPU batch serves all 49 callbacks
+        buf = np.frombuffer(data, dtype=np.uint8)
+        q.hintSource(st, buf.ctypes.data, buf.size, 0)
+        before = q.getStats(st)
+        r2 = oracle.compress_with_producer(buf, q.producer, st, chunk=len(data), level=3)
+        after = q.getStats(st)
+        q.hintSource(st, 0, 0, 0)
+        assert r2["round_trip"] and r2["errors"] == 0 and r2["csize"] == r["csize"]
+        assert after["batched"] - before["batched"] == 49
+    finally:
+        q.freeSeqProdState(st)
+        q.stopQatDevice()
+
+
+def test_producer_argument_rejection_on_gpu(pkg):
+    """Same rejections as the reference with a live device (/root/reference/src/qatseqprod.c:1123-1137)."""
+    q = pkg.QatSeqProd
+    assert q.startQatDevice() == pkg.QZSTD_OK
+    st = q.createSeqProdState()
+    try:
+        src = np.frombuffer(datagen.text_like(BLOCK, 3), dtype=np.uint8)
+        out = np.zeros((43691, 4), np.uint32)
+        ok = q.qatSequenceProducer(st, out.ctypes.data, 43691, src.ctypes.data, src.size, None, 0, 3, 1 << 17)
+        assert ok != pkg.ZSTD_SEQUENCE_PRODUCER_ERROR and ok > 1
+        E = pkg.ZSTD_SEQUENCE_PRODUCER_ERROR
+        assert q.qatSequenceProducer(st, out.ctypes.data, 43691, src.ctypes.data, src.size, None, 0, 0, 1 << 17) == E
+        assert q.qatSequenceProducer(st, out.ctypes.data, 43691, src.ctypes.data, src.size, None, 0, 13, 1 << 17) == E
+        assert q.qatSequenceProducer(st, out.ctypes.data, 43691, src.ctypes.data, src.size, src.ctypes.data, 0, 3, 1 << 17) == E
+        assert q.qatSequenceProducer(st, out.ctypes.data, 43691, src.ctypes.data, src.size, None, 8, 3, 1 << 17) == E
+        assert q.qatSequenceProducer(st, out.ctypes.data, 43691, src.ctypes.data, src.size, None, 0, 3, 1 << 14) == E
+        assert q.qatSequenceProducer(st, out.ctypes.data, 43691, src.ctypes.data, 1000, None, 0, 3, 1000) != E
+        assert q.qatSequenceProducer(st, out.ctypes.data, 10, src.ctypes.data, src.size, None, 0, 3, 1 << 17) == E
+    finally:
+        q.freeSeqProdState(st)
+        q.stopQatDevice()
