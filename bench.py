@@ -200,7 +200,11 @@ def main():
     seqs = torch.empty((n_blocks, pkg.SEQ_STRIDE, 4), dtype=torch.int32, device=dev)
     counts = torch.zeros(n_blocks, dtype=torch.int32, device=dev)
     eng = pkg.Engine(local)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream: the C-ABI launches on it and torch.cuda.Event times it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         eng.parse_device(src.data_ptr(), n_bytes, BLOCK, n_blocks, args.level, seqs.data_ptr(), counts.data_ptr(),

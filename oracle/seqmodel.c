@@ -10,7 +10,7 @@
  *                  and reads-then-overwrites one slot of each table: the candidate is the most
  *                  recent earlier position with the same hash.
  *   2. extension   common prefix of src[p..] and src[cand..]: candidates are ranked on their first
- *                  32 bytes, the winner is extended up to extCap (and never past n).
+ *                  16 bytes, the winner is extended up to extCap (and never past n).
  *   3. propagation B(p) = the match, among all starting at q <= p, that reaches farthest right.
  *   4. parse       greedy left-to-right over B with lazy look-ahead; zero-literal sequences
  *                  repeating the previous offset are merged into their predecessor; the last
@@ -22,7 +22,7 @@
 #include <string.h>
 
 #define MODEL_MAX_BLOCK (1u << 17)
-#define MODEL_PROBE     32u          /* bytes compared per candidate before a winner is picked */
+#define MODEL_PROBE     16u          /* bytes compared per candidate before a winner is picked */
 
 static inline uint32_t rd32(const uint8_t *p)
 {
@@ -59,7 +59,7 @@ void seqmodel_params_for_level(int level, SeqModelParams *prm)
     prm->minMatch = 4;
     prm->extCap = 256;
     prm->lazyDepth = 1;
-    prm->window = 1024;
+    prm->window = 32;            /* lazy look-ahead stays inside the 32-position group one warp owns */
     if (level <= 2) {            /* fast class */
         prm->shortBytes = 6;
         prm->lazyDepth = 0;
@@ -109,21 +109,24 @@ size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t o
             tabS[hS] = (uint16_t)(p >> 1);
             uint32_t lim = N - p;
             if (lim > (uint32_t)prm->extCap) lim = (uint32_t)prm->extCap;
-            /* Phase 1: every candidate is measured over its first PROBE bytes only; candidate
-             * order is long pair (even, odd) then short pair; a later candidate replaces the best
-             * so far if it is longer, or as long and nearer.
+            /* Phase 1: each table contributes ONE candidate: of the two positions its slot stands
+             * for (2v, 2v+1) the one whose first 4 bytes equal ours, the nearer one if both do.  It is
+             * measured over its first PROBE bytes only.  The short-table candidate replaces the
+             * long-table one if it is longer, or as long and nearer.
              * Phase 2: only the winner is extended, up to extCap. */
             const uint32_t probe = lim < MODEL_PROBE ? lim : MODEL_PROBE;
+            const uint32_t a4 = rd32(src + p);
             for (int t = 0; t < 2; t++) {
-                for (uint32_t k = 0; k < 2; k++) {
-                    const uint32_t q = base[t] + k;
-                    if (q >= p) continue;
-                    const uint8_t *a = src + p, *b = src + q;
-                    uint32_t ml = 0;
-                    while (ml < probe && a[ml] == b[ml]) ml++;
-                    const uint32_t off = p - q;
-                    if (ml > bestLen || (ml == bestLen && ml > 0 && off < bestOff)) { bestLen = ml; bestOff = off; }
-                }
+                const uint32_t q0 = base[t];
+                uint32_t q = UINT32_MAX;
+                if (q0 < p && rd32(src + q0) == a4) q = q0;
+                if (q0 + 1 < p && rd32(src + q0 + 1) == a4) q = q0 + 1;
+                if (q == UINT32_MAX) continue;
+                const uint8_t *a = src + p, *b = src + q;
+                uint32_t ml = 4;
+                while (ml < probe && a[ml] == b[ml]) ml++;
+                const uint32_t off = p - q;
+                if (ml > bestLen || (ml == bestLen && off < bestOff)) { bestLen = ml; bestOff = off; }
             }
             if (bestLen == MODEL_PROBE) {
                 const uint8_t *a = src + p, *b = src + p - bestOff;

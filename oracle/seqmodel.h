@@ -33,7 +33,7 @@ typedef struct {
     int minMatch;     /* shortest match the parser may emit (>= 3)                  */
     int extCap;       /* per-position extension cap in bytes (multiple of 4)        */
     int lazyDepth;    /* 0 greedy, 1 lazy, 2 lazy2                                  */
-    int window;       /* pipeline window in positions: lazy look-ahead never crosses a multiple of it */
+    int window;       /* lazy look-ahead never crosses a multiple of it (32 = one warp's group)   */
 } SeqModelParams;
 
 /* Parameters the kernels use for a zstd compression level (1..12). */

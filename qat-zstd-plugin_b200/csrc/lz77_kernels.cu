@@ -80,6 +80,14 @@ __device__ __forceinline__ uint32_t ld32u(const uint32_t *in32, uint32_t bytePos
     return __funnelshift_r(in32[w], in32[w + 1], (bytePos & 3u) * 8u);
 }
 
+// Warp-uniform pop from a shared-memory task counter: one ATOMS by lane 0, one broadcast.
+__device__ __forceinline__ uint32_t pop_task(uint32_t ctrAddr, uint32_t lane)
+{
+    uint32_t id = 0;
+    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(id) : "r"(ctrAddr) : "memory");
+    return __shfl_sync(0xFFFFFFFFu, id, 0);
+}
+
 __device__ __forceinline__ uint32_t ring_index(uint32_t group, uint32_t lane)
 {
     return group * 32u + (lane ^ group);   // XOR swizzle: conflict-free by group and by lane
@@ -96,10 +104,10 @@ struct Shared {
     uint16_t *tabS;
     uint32_t *ring0;    // [kRing][kWindow]
     uint32_t *ring1;    // [kRing][kWindow]
-    uint32_t *mask;     // [kRing][kGroups]
-    uint32_t *carry;    // [kGroups + 1][2]
+    uint32_t *gmax;     // [kRing][kGroups] packed farthest-reaching match of each group
     uint64_t *mbar;     // [kTmaChunks]
     volatile int *work; // next block index
+    unsigned int *task; // [2][2] per-stage task counters of the hash/extend warps (double-buffered)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -171,16 +179,15 @@ __device__ __forceinline__ void stage_table(uint32_t *ring, uint16_t *tab, uint3
 // E: candidates of one group -> best match per position -> prefix-max of match ends
 // ring out: ring0 = end (p + len, 0 if none so far in this group), ring1 = offset
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t probe_len(const uint32_t *in32, uint32_t p, uint32_t q, uint32_t probe)
+__device__ __forceinline__ uint32_t first_diff_16(uint32_t x1, uint32_t x2, uint32_t x3)
 {
-    // caller has already established that the first 4 bytes are equal
-    uint32_t k = 4;
-    while (k < probe) {
-        const uint32_t x = ld32u(in32, p + k) ^ ld32u(in32, q + k);
-        if (x) { k += (__ffs(x) - 1) >> 3; break; }
-        k += 4;
-    }
-    return k < probe ? k : probe;
+    // length of the common prefix of two 16-byte strings whose first 4 bytes are equal,
+    // given the XOR of words 1..3 (branch-free)
+    uint32_t len = 16u;
+    if (x3) len = 12u + ((__ffs(x3) - 1) >> 3);
+    if (x2) len = 8u + ((__ffs(x2) - 1) >> 3);
+    if (x1) len = 4u + ((__ffs(x1) - 1) >> 3);
+    return len;
 }
 
 __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t slot, uint32_t group, uint32_t lane,
@@ -190,30 +197,34 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t slot, uin
     const uint32_t idx = slot * kWindow + ring_index(group, lane);
     const uint32_t cL = S.ring0[idx], cS = S.ring1[idx];
     const uint32_t *in32 = S.in32;
-    uint32_t bestLen = 0, bestOff = 0, lim = 0;
-    if (p < nh) {
-        lim = min(n - p, extCap);
-        const uint32_t probe = min(lim, kProbe);
-        const uint32_t a0 = ld32u(in32, p);
+    const bool valid = p < nh;
+    uint32_t bestLen = 0, bestOff = 0;
+    const uint32_t lim = valid ? min(n - p, extCap) : 0u;
+    const uint32_t probe = min(lim, kProbe);
+    // our own first 16 bytes, as four unaligned words (reads stay inside the padded buffer)
+    uint32_t a0, a1, a2, a3;
+    {
+        const uint32_t w = min(p, kBlockMax) >> 2, sh = (p & 3u) * 8u;
+        const uint32_t x0 = in32[w], x1 = in32[w + 1], x2 = in32[w + 2], x3 = in32[w + 3], x4 = in32[w + 4];
+        a0 = __funnelshift_r(x0, x1, sh); a1 = __funnelshift_r(x1, x2, sh);
+        a2 = __funnelshift_r(x2, x3, sh); a3 = __funnelshift_r(x3, x4, sh);
+    }
 #pragma unroll
-        for (int t = 0; t < 2; t++) {
-            const uint32_t c = t ? cS : cL;
-            if (t && cS == cL) break;
-            const uint32_t q0 = 2u * c;
-            if (q0 >= p) continue;                              // also rejects the 0xFFFF empty marker
-            const uint32_t w = q0 >> 2, sh = (q0 & 3u) * 8u;    // q0 is even: sh is 0 or 16
-            const uint32_t x = in32[w], y = in32[w + 1];
-            const uint32_t b0 = __funnelshift_r(x, y, sh);
-            const uint32_t b1 = __funnelshift_r(x, y, sh + 8u);
-            if (b0 == a0) {
-                const uint32_t ml = probe_len(in32, p, q0, probe), off = p - q0;
-                if (ml > bestLen || (ml == bestLen && off < bestOff)) { bestLen = ml; bestOff = off; }
-            }
-            if (q0 + 1 < p && b1 == a0) {
-                const uint32_t ml = probe_len(in32, p, q0 + 1, probe), off = p - q0 - 1;
-                if (ml > bestLen || (ml == bestLen && off < bestOff)) { bestLen = ml; bestOff = off; }
-            }
-        }
+    for (int t = 0; t < 2; t++) {
+        const uint32_t c = t ? cS : cL;
+        // the slot stands for positions 2c and 2c+1 (same 32-bit word row): pick the one whose first
+        // 4 bytes equal ours, the nearer one if both do.  0xFFFF (empty) fails q0 < p by construction.
+        const uint32_t q0 = 2u * c;
+        const uint32_t w = min(q0, kBlockMax) >> 2, sh0 = (q0 & 3u) * 8u;       // q0 even: sh0 is 0 or 16
+        const uint32_t y0 = in32[w], y1 = in32[w + 1], y2 = in32[w + 2], y3 = in32[w + 3], y4 = in32[w + 4];
+        const bool c0 = valid && q0 < p && __funnelshift_r(y0, y1, sh0) == a0;
+        const bool c1 = valid && q0 + 1u < p && __funnelshift_r(y0, y1, sh0 + 8u) == a0;
+        const uint32_t sh = sh0 + (c1 ? 8u : 0u);
+        const uint32_t b1 = __funnelshift_r(y1, y2, sh), b2 = __funnelshift_r(y2, y3, sh), b3 = __funnelshift_r(y3, y4, sh);
+        uint32_t ml = min(first_diff_16(a1 ^ b1, a2 ^ b2, a3 ^ b3), probe);
+        const uint32_t off = p - q0 - (c1 ? 1u : 0u);
+        if (!(c0 || c1)) ml = 0;
+        if (ml > bestLen || (ml == bestLen && ml > 0 && off < bestOff)) { bestLen = ml; bestOff = off; }
     }
 
     // Long extension of winners that filled the probe.  A lane continuing its predecessor's
@@ -248,20 +259,78 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t slot, uin
         }
         if (myHead == h) bestLen = min(lim, U - (lane - h));
     }
-    if (bestLen < minMatch) bestLen = 0;
-
-    // inclusive prefix-max over the group; strictly greater replaces, ties keep the older match
-    uint32_t end = bestLen ? p + bestLen : 0u, off = bestOff;
+    // Pack {end relative to the group start (9 bits), 31 - lane (6 bits), offset (17 bits)}: an unsigned
+    // max over packed words picks the farthest-reaching match and, on ties, the older one.
+    uint32_t pk = 0;
+    if (bestLen >= minMatch) pk = ((lane + bestLen) << 23) | ((31u - lane) << 17) | bestOff;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t oe = __shfl_up_sync(0xFFFFFFFFu, end, d);
-        const uint32_t oo = __shfl_up_sync(0xFFFFFFFFu, off, d);
-        if (lane >= static_cast<uint32_t>(d) && !(end > oe)) { end = oe; off = oo; }
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pk, d);
+        if (lane >= static_cast<uint32_t>(d)) pk = max(pk, o);
     }
-    S.ring0[idx] = end;
-    S.ring1[idx] = off;
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, end >= p + minMatch);
-    if (lane == 0) S.mask[slot * kGroups + group] = m;
+    S.ring0[idx] = pk;                                   // prefix-max within the group
+    if (lane == 31) S.gmax[slot * kGroups + group] = pk; // the group's total, for the carry of later groups
+}
+
+// ------------------------------------------------------------------------------------------
+// J: jump links of one group.  Folds the carry of the previous 8 groups (a match is at most
+// extCap = 256 bytes long, so nothing older can reach in) into the group's prefix-max, applies the
+// lazy rule, and leaves one word per position: {target - windowBase (11 bits), kind (2), offset (17)}.
+//   SKIP  no usable match here: go to the next position of the group that has one (or to its end)
+//   HOP   a later start is better (lazy): go to p+1 / p+2
+//   TAKE  emit the match [p, target) at `offset`
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kKindSkip = 0, kKindHop = 1, kKindTake = 2;
+
+__device__ __forceinline__ void stage_jump(const Shared &S, uint32_t wdx, uint32_t group, uint32_t lane,
+                                           uint32_t minMatch, uint32_t lazyDepth)
+{
+    const uint32_t slot = wdx & (kRing - 1);
+    const uint32_t idx = slot * kWindow + ring_index(group, lane);
+    // ---- carry: lane k-1 looks k groups back (possibly into the previous window's slot)
+    uint32_t c = 0;
+    if (lane < 8) {
+        const uint32_t k = lane + 1;
+        int gg = static_cast<int>(group) - static_cast<int>(k);
+        uint32_t sl = slot;
+        bool ok = true;
+        if (gg < 0) { ok = wdx > 0; gg += kGroups; sl = (wdx - 1) & (kRing - 1); }
+        if (ok) {
+            const uint32_t v = S.gmax[sl * kGroups + gg];
+            const uint32_t rel = v >> 23;
+            if (rel > 32u * k) c = ((rel - 32u * k) << 23) | ((32u + k) << 17) | (v & 0x1FFFFu);
+        }
+    }
+    c = __reduce_max_sync(0xFFFFFFFFu, c);
+    const uint32_t bt = max(S.ring0[idx], c);              // B(p): farthest-reaching match covering p
+    const uint32_t rel = bt >> 23, off = bt & 0x1FFFFu;
+    const bool has = rel >= lane + minMatch;
+    const int32_t gain = static_cast<int32_t>((rel - lane) * 4u) - static_cast<int32_t>(31 - __clz(off + 1u));
+
+    // ---- B(p+1), B(p+2) by shuffle.  The look-ahead never leaves the group (model: window = 32).
+    const uint32_t b1 = __shfl_down_sync(0xFFFFFFFFu, bt, 1), b2 = __shfl_down_sync(0xFFFFFFFFu, bt, 2);
+    const uint32_t l1 = lane + 1, l2 = lane + 2;
+    const bool ok1 = lane < 31 && (b1 >> 23) >= l1 + minMatch;
+    const bool ok2 = lane < 30 && (b2 >> 23) >= l2 + minMatch;
+    const int32_t gain1 = static_cast<int32_t>(((b1 >> 23) - l1) * 4u) - static_cast<int32_t>(31 - __clz((b1 & 0x1FFFFu) + 1u));
+    const int32_t gain2 = static_cast<int32_t>(((b2 >> 23) - l2) * 4u) - static_cast<int32_t>(31 - __clz((b2 & 0x1FFFFu) + 1u));
+    uint32_t adv = 0;
+    if (has && lazyDepth >= 1 && ok1) {
+        if (gain1 > gain + 4) adv = 1;
+        else if (lazyDepth >= 2 && ok2 && gain2 > gain + 7) adv = 2;
+    }
+    const uint32_t hasMask = __ballot_sync(0xFFFFFFFFu, has);
+    const uint32_t groupRel = group * 32u;                  // group start relative to the window
+    uint32_t tgt, kind;
+    if (has) {
+        kind = adv ? kKindHop : kKindTake;
+        tgt = groupRel + (adv ? lane + adv : rel);
+    } else {
+        const uint32_t m = hasMask & ~((2u << lane) - 1u);
+        kind = kKindSkip;
+        tgt = groupRel + (m ? __ffs(m) - 1 : 32u);
+    }
+    S.ring0[idx] = tgt | (kind << 11) | (off << 13);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -272,7 +341,6 @@ struct ParseCarry {          // uniform across the warp, carried from window to 
     uint32_t anchor;         // end of the last emitted match
     uint32_t prevOff;        // offset of the last emitted match
     uint32_t nOut;           // sequences written so far
-    uint32_t runEnd, runOff; // farthest-reaching match seen so far (propagated B)
 };
 
 struct LaneWalk {
@@ -283,110 +351,57 @@ struct LaneWalk {
     uint32_t lastEnd, lastOff;
 };
 
-__device__ __forceinline__ void best_at(const Shared &S, uint32_t slot, uint32_t q, uint32_t &e, uint32_t &o)
-{
-    const uint32_t g = (q >> 5) & (kGroups - 1), l = q & 31u;
-    const uint32_t idx = slot * kWindow + ring_index(g, l);
-    e = S.ring0[idx];
-    o = S.ring1[idx];
-    const uint32_t ce = S.carry[2 * g], co = S.carry[2 * g + 1];
-    if (!(e > ce)) { e = ce; o = co; }
-}
-
-// Walks the lane's segment from `entry`.  When `out` is non-null the matches are also emitted:
-// new sequences go to out[idx...], a leading continuation of the previous sequence is returned in
-// `headAdd` (to be added to out[firstIdx - 1].matchLength by the caller).
+// Chases the jump links of the lane's segment (= one group) from `entry`.  In emit mode the matches
+// are also written: new sequences go to out[outIdx...]; a leading continuation of the previous
+// sequence is returned in `headAdd` (the caller adds it to out[firstIdx - 1].matchLength).
 template <bool kEmit>
-__device__ __forceinline__ void lane_walk(const Shared &S, uint32_t slot, uint32_t segStart, uint32_t mask,
-                                          uint32_t entry, uint32_t minMatch, uint32_t lazyDepth,
-                                          LaneWalk &r, uint32_t anchor, uint32_t prevOff,
+__device__ __forceinline__ void lane_walk(const uint32_t *links, uint32_t base, uint32_t group,
+                                          uint32_t entry, LaneWalk &r, uint32_t anchor, uint32_t prevOff,
                                           uint4 *out, uint32_t outIdx, uint32_t &headAdd)
 {
+    const uint32_t segStart = base + group * 32u, segEnd = segStart + 32u;
     uint32_t c = entry;
     r.cnt = 0; r.merges = 0; r.firstPos = 0; r.firstOff = 0; r.lastEnd = 0; r.lastOff = 0;
     uint32_t openOff = 0, openLit = 0, openLen = 0;   // sequence being accumulated (emit mode)
     bool haveOpen = false;
     headAdd = 0;
-    const uint32_t segEnd = segStart + 32u;
     while (c < segEnd) {
-        const uint32_t m = mask & (0xFFFFFFFFu << (c - segStart));
-        if (!m) { c = segEnd; break; }
-        uint32_t p = segStart + __ffs(m) - 1;
-        uint32_t e, o;
-        best_at(S, slot, p, e, o);
-        if (lazyDepth >= 1) {
-            for (;;) {
-                const int32_t g0 = gain_of(e - p, o);
-                uint32_t q = p + 1, e1, o1;
-                if ((q & (kWindow - 1)) == 0) break;
-                best_at(S, slot, q, e1, o1);
-                if (e1 < q + minMatch) break;
-                if (gain_of(e1 - q, o1) > g0 + 4) { p = q; e = e1; o = o1; continue; }
-                if (lazyDepth < 2) break;
-                q = p + 2;
-                if ((q & (kWindow - 1)) == 0) break;
-                best_at(S, slot, q, e1, o1);
-                if (e1 < q + minMatch) break;
-                if (gain_of(e1 - q, o1) > g0 + 7) { p = q; e = e1; o = o1; continue; }
-                break;
+        const uint32_t w = links[ring_index(group, c - segStart)];
+        const uint32_t tgt = base + (w & 0x7FFu);
+        if (((w >> 11) & 3u) == kKindTake) {
+            const uint32_t o = w >> 13;
+            if (r.cnt == 0) { r.firstPos = c; r.firstOff = o; }
+            else if (c == r.lastEnd && o == r.lastOff) r.merges++;
+            r.cnt++;
+            if (kEmit) {
+                const uint32_t lit = c - anchor, len = tgt - c;
+                if (lit == 0 && o == prevOff && anchor > 0) {
+                    if (haveOpen) openLen += len; else headAdd += len;
+                } else {
+                    if (haveOpen) out[outIdx++] = make_uint4(openOff, openLit, openLen, 0u);
+                    openOff = o; openLit = lit; openLen = len; haveOpen = true;
+                }
+                anchor = tgt; prevOff = o;
             }
+            r.lastEnd = tgt; r.lastOff = o;
         }
-        // take the match [p, e) at offset o
-        if (r.cnt == 0) { r.firstPos = p; r.firstOff = o; }
-        else if (p == r.lastEnd && o == r.lastOff) r.merges++;
-        r.cnt++;
-        if (kEmit) {
-            const uint32_t lit = p - anchor, len = e - p;
-            if (lit == 0 && o == prevOff && anchor > 0) {
-                if (haveOpen) openLen += len; else headAdd += len;
-            } else {
-                if (haveOpen) out[outIdx++] = make_uint4(openOff, openLit, openLen, 0u);
-                openOff = o; openLit = lit; openLen = len; haveOpen = true;
-            }
-            anchor = e; prevOff = o;
-        }
-        r.lastEnd = e; r.lastOff = o;
-        c = e;
+        c = tgt;
     }
     if (kEmit && haveOpen) out[outIdx] = make_uint4(openOff, openLit, openLen, 0u);
     r.exit = c;
 }
 
 __device__ __forceinline__ void stage_parse(const Shared &S, uint32_t slot, uint32_t lane, uint32_t base,
-                                            uint32_t minMatch, uint32_t lazyDepth, ParseCarry &pc, uint4 *out)
+                                            ParseCarry &pc, uint4 *out)
 {
+    const uint32_t *links = S.ring0 + slot * kWindow;
     const uint32_t segStart = base + lane * 32u;
-    // ---- carry of the propagated best match into every group
-    const uint32_t i31 = slot * kWindow + ring_index(lane, 31u);
-    uint32_t incE = S.ring0[i31], incO = S.ring1[i31];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t oe = __shfl_up_sync(0xFFFFFFFFu, incE, d);
-        const uint32_t oo = __shfl_up_sync(0xFFFFFFFFu, incO, d);
-        if (lane >= static_cast<uint32_t>(d) && !(incE > oe)) { incE = oe; incO = oo; }
-    }
-    uint32_t exE = __shfl_up_sync(0xFFFFFFFFu, incE, 1), exO = __shfl_up_sync(0xFFFFFFFFu, incO, 1);
-    if (lane == 0 || !(exE > pc.runEnd)) { exE = pc.runEnd; exO = pc.runOff; }
-    S.carry[2 * lane] = exE;
-    S.carry[2 * lane + 1] = exO;
-    {
-        uint32_t tE = __shfl_sync(0xFFFFFFFFu, incE, 31), tO = __shfl_sync(0xFFFFFFFFu, incO, 31);
-        if (tE > pc.runEnd) { pc.runEnd = tE; pc.runOff = tO; }
-    }
-    __syncwarp();
-
-    // ---- positions of this segment that have a usable match
-    uint32_t mask = S.mask[slot * kGroups + lane];
-    if (exE >= segStart + minMatch) {
-        const uint32_t cnt = exE - minMatch - segStart + 1u;
-        mask |= cnt >= 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u);
-    }
 
     // ---- speculative parse, iterated until every lane's entry equals its predecessor's exit
     LaneWalk w;
     uint32_t dummy;
     uint32_t entry = lane == 0 ? max(pc.cursor, base) : segStart;
-    lane_walk<false>(S, slot, segStart, mask, entry, minMatch, lazyDepth, w, 0, 0, nullptr, 0, dummy);
+    lane_walk<false>(links, base, lane, entry, w, 0, 0, nullptr, 0, dummy);
     for (;;) {
         const uint32_t prevExit = __shfl_up_sync(0xFFFFFFFFu, w.exit, 1);
         const uint32_t want = lane == 0 ? entry : max(prevExit, segStart);
@@ -394,7 +409,7 @@ __device__ __forceinline__ void stage_parse(const Shared &S, uint32_t slot, uint
         if (!__any_sync(0xFFFFFFFFu, changed)) break;
         if (changed) {
             entry = want;
-            lane_walk<false>(S, slot, segStart, mask, entry, minMatch, lazyDepth, w, 0, 0, nullptr, 0, dummy);
+            lane_walk<false>(links, base, lane, entry, w, 0, 0, nullptr, 0, dummy);
         }
     }
 
@@ -425,7 +440,7 @@ __device__ __forceinline__ void stage_parse(const Shared &S, uint32_t slot, uint
     uint32_t headAdd = 0;
     if (w.cnt) {
         LaneWalk w2;
-        lane_walk<true>(S, slot, segStart, mask, entry, minMatch, lazyDepth, w2, anchor, prevOff, out, firstIdx, headAdd);
+        lane_walk<true>(links, base, lane, entry, w2, anchor, prevOff, out, firstIdx, headAdd);
     }
     __syncwarp();
     if (headAdd) atomicAdd(&out[firstIdx - 1].z, headAdd);   // continuation of an earlier lane's sequence
@@ -450,10 +465,10 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         S.tabS = reinterpret_cast<uint16_t *>(p);  p += kSmemTabS;
         S.ring0 = reinterpret_cast<uint32_t *>(p); p += kSmemRing / 2;
         S.ring1 = reinterpret_cast<uint32_t *>(p); p += kSmemRing / 2;
-        S.mask = reinterpret_cast<uint32_t *>(p);  p += kSmemMask;
-        S.carry = reinterpret_cast<uint32_t *>(p); p += kSmemCarry;
+        S.gmax = reinterpret_cast<uint32_t *>(p);  p += kSmemGmax;
         S.mbar = reinterpret_cast<uint64_t *>(p);  p += kTmaChunks * 8;
-        S.work = reinterpret_cast<volatile int *>(p);
+        S.work = reinterpret_cast<volatile int *>(p);  p += 8;
+        S.task = reinterpret_cast<unsigned int *>(p);
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
@@ -500,40 +515,65 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
             const uint4 ff = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             for (uint32_t i = tid; i < (kSmemTabL + kSmemTabS) / 16; i += kThreads) t[i] = ff;
         }
+        if (tid < 4) S.task[tid] = 0u;
         __syncthreads();
 
         const uint32_t nh = n >= 8 ? n - 7 : 0;
         const uint32_t nW = (n + kWindow - 1) / kWindow;
         uint32_t chunksSeen = 0;
-        ParseCarry pc = {0, 0, 0, 0, 0, 0};
+        ParseCarry pc = {0, 0, 0, 0};
 
+        unsigned long long busy = 0, blockStart = clock64();
         for (uint32_t t = 0; t < nW + 3; t++) {
+            const unsigned long long c0 = clock64();
             if (warp < kEhWarps) {
                 // bytes this stage may touch: hashing window t reads < (t+1)*1024 + 11, extending
                 // window t-2 reads < (t-1)*1024 + extCap + 36 + 3
                 const uint32_t need = min(bulk, (t + 1) * kWindow + 16u);
                 const uint32_t wantChunks = (need + kTmaChunk - 1) / kTmaChunk;
                 while (chunksSeen < wantChunks) { mbar_wait(smem_u32(&S.mbar[chunksSeen]), (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
-                if (t >= 2 && t - 2 < nW) {
-                    const uint32_t wdx = t - 2, slot = wdx & (kRing - 1);
-                    for (uint32_t g = warp; g < kGroups; g += kEhWarps)
-                        stage_extend(S, slot, g, lane, wdx * kWindow + g * 32u + lane, n, nh, P.minMatch, P.extCap);
+                // queue A: extension groups of window t-2 (heavier, first), then hash groups of window t
+                const bool haveE = t >= 2 && t - 2 < nW;
+                const uint32_t nE = haveE ? kGroups : 0u;
+                const uint32_t nA = nE + (t < nW ? kGroups : 0u);
+                const uint32_t ctrA = smem_u32(&S.task[(t & 1u) * 2u]), ctrB = ctrA + 4u;
+                for (;;) {
+                    const uint32_t id = pop_task(ctrA, lane);
+                    if (id >= nA) break;
+                    if (id < nE) {
+                        const uint32_t wdx = t - 2;
+                        stage_extend(S, wdx & (kRing - 1), id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap);
+                    } else {
+                        const uint32_t g = id - nE;
+                        stage_hash(S, t & (kRing - 1), g, lane, t * kWindow + g * 32u + lane, nh, P.shortMask);
+                    }
                 }
-                if (t < nW) {
-                    const uint32_t slot = t & (kRing - 1);
-                    for (uint32_t g = warp; g < kGroups; g += kEhWarps)
-                        stage_hash(S, slot, g, lane, t * kWindow + g * 32u + lane, nh, P.shortMask);
+                // all extension groups of window t-2 are done (hash/extend warps only): queue B, jump links
+                asm volatile("bar.sync 1, %0;" ::"n"(kEhWarps * 32) : "memory");
+                if (haveE) {
+                    for (;;) {
+                        const uint32_t id = pop_task(ctrB, lane);
+                        if (id >= kGroups) break;
+                        stage_jump(S, t - 2, id, lane, P.minMatch, P.lazyDepth);
+                    }
                 }
             } else if (warp == kWarpTabL) {
                 if (t >= 1 && t - 1 < nW) stage_table(S.ring0, S.tabL, (t - 1) & (kRing - 1), lane, (t - 1) * kWindow);
             } else if (warp == kWarpTabS) {
                 if (t >= 1 && t - 1 < nW) stage_table(S.ring1, S.tabS, (t - 1) & (kRing - 1), lane, (t - 1) * kWindow);
             } else {
-                if (t >= 3) stage_parse(S, (t - 3) & (kRing - 1), lane, (t - 3) * kWindow, P.minMatch, P.lazyDepth, pc, out);
+                if (lane < 2) S.task[((t + 1u) & 1u) * 2u + lane] = 0u;   // next stage's queues (nobody touches them now)
+                if (t >= 3) stage_parse(S, (t - 3) & (kRing - 1), lane, (t - 3) * kWindow, pc, out);
             }
+            busy += clock64() - c0;
             __syncthreads();
         }
 
+        if (P.roleCycles && lane == 0) {
+            const int role = warp < kEhWarps ? 0 : (warp - kEhWarps + 1);
+            atomicAdd(&P.roleCycles[role], busy);
+            if (warp == kWarpParse) { atomicAdd(&P.roleCycles[4], clock64() - blockStart); atomicAdd(&P.roleCycles[5], (unsigned long long)(nW + 3)); }
+        }
         if (warp == kWarpParse && lane == 0) {
             out[pc.nOut] = make_uint4(0u, n - pc.anchor, 0u, 0u);   // trailing literals / block delimiter
             P.counts[b] = pc.nOut + 1u;

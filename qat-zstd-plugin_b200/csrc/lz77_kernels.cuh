@@ -18,13 +18,13 @@ constexpr uint32_t kGroups        = kWindow / 32;
 constexpr uint32_t kRing          = 4;          // windows in flight: hash, table, extend, parse
 constexpr uint32_t kLongBits      = 14;
 constexpr uint32_t kShortBits     = 14;
-constexpr uint32_t kProbe         = 32;         // bytes compared per candidate before a winner is picked
+constexpr uint32_t kProbe         = 16;         // bytes compared per candidate before a winner is picked
 constexpr uint32_t kMaxExtCap     = 256;
 constexpr uint32_t kInputPad      = 320;        // readable slack after the block in shared memory
 constexpr uint32_t kTmaChunk      = 16384;
 constexpr uint32_t kTmaChunks     = kBlockMax / kTmaChunk;
 
-constexpr int kEhWarps   = 16;                  // hash + extension warps
+constexpr int kEhWarps   = 29;                  // hash + extension warps
 constexpr int kWarpTabL  = kEhWarps;            // serial owner of the long-hash table
 constexpr int kWarpTabS  = kEhWarps + 1;        // serial owner of the short-hash table
 constexpr int kWarpParse = kEhWarps + 2;        // speculative lane-parallel parser + emitter
@@ -36,10 +36,9 @@ constexpr uint32_t kSmemInput   = kBlockMax + kInputPad;
 constexpr uint32_t kSmemTabL    = (1u << kLongBits) * 2;
 constexpr uint32_t kSmemTabS    = (1u << kShortBits) * 2;
 constexpr uint32_t kSmemRing    = kRing * 2 * kWindow * 4;
-constexpr uint32_t kSmemMask    = kRing * kGroups * 4;
-constexpr uint32_t kSmemCarry   = (kGroups + 1) * 2 * 4;
-constexpr uint32_t kSmemMisc    = 128;          // mbarriers + work-item slot
-constexpr uint32_t kSmemTotal   = kSmemInput + kSmemTabL + kSmemTabS + kSmemRing + kSmemMask + kSmemCarry + kSmemMisc;
+constexpr uint32_t kSmemGmax    = kRing * kGroups * 4;
+constexpr uint32_t kSmemMisc    = 128;          // mbarriers + work-item slot + task counters
+constexpr uint32_t kSmemTotal   = kSmemInput + kSmemTabL + kSmemTabS + kSmemRing + kSmemGmax + kSmemMisc;
 static_assert(kSmemTotal <= 232448, "exceeds 227 KB of shared memory per CTA");
 
 struct ParseParams {
@@ -57,6 +56,7 @@ struct ParseParams {
     uint32_t minMatch;         // >= 4
     uint32_t extCap;           // <= kMaxExtCap
     uint32_t lazyDepth;        // 0..2
+    unsigned long long *roleCycles; // optional (may be null): per-role busy cycles, developer profiling
 };
 
 // Fills the per-level fields of ParseParams. Returns false for levels outside 1..12

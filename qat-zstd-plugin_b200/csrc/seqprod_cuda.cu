@@ -230,6 +230,7 @@ int b200sp_engine_create(int device, b200sp_engine **out)
     e->numSMs = prop.multiProcessorCount;
     ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaMalloc(&e->d_work, 256);
+    if (ce == cudaSuccess) ce = cudaMemset(e->d_work, 0, 256);
     if (ce != cudaSuccess) { b200sp_engine_destroy(e); return fail(B200SP_ECUDA, "engine_create", ce); }
     *out = e;
     return B200SP_OK;
@@ -287,6 +288,9 @@ int b200sp_parse_device(b200sp_engine *e, const void *d_src, uint64_t totalSize,
     p.seqStride = seqStride;
     p.counts = d_counts;
     p.workCounter = e->d_work;
+    // developer profiling: B200SP_ROLE_PROFILE=1 accumulates per-role busy cycles in d_work[8..]
+    static const bool roleProfile = getenv("B200SP_ROLE_PROFILE") != nullptr;
+    p.roleCycles = roleProfile ? reinterpret_cast<unsigned long long *>(e->d_work) + 1 : nullptr;
     CU_TRY(cudaMemsetAsync(e->d_work, 0, sizeof(unsigned int), st), "cudaMemsetAsync(work counter)");
     CU_TRY(b200sp::launch_parse(p, e->numSMs, st), "launch lz77_parse_kernel");
     return B200SP_OK;
@@ -309,6 +313,16 @@ int b200sp_verify_device(b200sp_engine *e, const void *d_src, uint64_t totalSize
                                            d_sizes, nBlocks, reinterpret_cast<const uint4 *>(d_seqs), seqStride,
                                            d_counts, d_bad);
     CU_TRY(cudaGetLastError(), "launch verify_kernel");
+    return B200SP_OK;
+}
+
+/* developer profiling (not in the public header): copies the 6 role counters and zeroes them */
+int b200sp_debug_role_cycles(b200sp_engine *e, unsigned long long *out6)
+{
+    if (!e || !out6) return B200SP_EINVAL;
+    cudaStreamSynchronize(e->stream);
+    cudaMemcpy(out6, reinterpret_cast<unsigned long long *>(e->d_work) + 1, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemset(reinterpret_cast<unsigned long long *>(e->d_work) + 1, 0, 6 * sizeof(unsigned long long));
     return B200SP_OK;
 }
 
