@@ -331,6 +331,34 @@ __device__ __forceinline__ void stage_jump(const Shared &S, uint32_t wdx, uint32
         tgt = groupRel + (m ? __ffs(m) - 1 : 32u);
     }
     S.ring0[idx] = tgt | (kind << 11) | (off << 13);
+
+    // ---- path summaries by pointer doubling.  For a cursor standing on this position: where the
+    // walk leaves the group, how many matches it takes, how many of them absorb their successor
+    // (zero literals, same offset), and which lanes hold the first / last taken match.
+    //   word = next (9 bits, >= 32: left the group, relative to the group start) | taken (4) |
+    //          absorbed (4) | first lane (6, 32 = none) | last lane (6, 32 = none)
+    const uint32_t nxt = tgt - groupRel;                              // 1 .. 32 + 256
+    const bool take = kind == kKindTake;
+    uint32_t absorb = 0;
+    {
+        const uint32_t succ = __shfl_sync(0xFFFFFFFFu, S.ring0[idx], nxt & 31u);   // link word of the node at our target
+        absorb = take && nxt < 32u && ((succ >> 11) & 3u) == kKindTake && (succ >> 13) == off;
+    }
+    uint32_t pk = nxt | ((take ? 1u : 0u) << 9) | (absorb << 13) | ((take ? lane : 32u) << 17) | ((take ? lane : 32u) << 23);
+#pragma unroll 1
+    for (int round = 0; round < 5; round++) {
+        const uint32_t cur = pk & 0x1FFu;
+        if (__all_sync(0xFFFFFFFFu, cur >= 32u)) break;
+        const uint32_t o = __shfl_sync(0xFFFFFFFFu, pk, cur & 31u);
+        if (cur < 32u) {
+            const uint32_t ft = (pk >> 17) & 63u, olt = (o >> 23) & 63u;
+            const uint32_t nft = ft < 32u ? ft : (o >> 17) & 63u;
+            const uint32_t nlt = olt < 32u ? olt : (pk >> 23) & 63u;
+            const uint32_t cnts = ((pk >> 9) & 0xFFu) + ((o >> 9) & 0xFFu);   // taken | absorbed << 4, no carry: <= 8 each
+            pk = (o & 0x1FFu) | (cnts << 9) | (nft << 17) | (nlt << 23);
+        }
+    }
+    S.ring1[idx] = pk;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -343,78 +371,77 @@ struct ParseCarry {          // uniform across the warp, carried from window to 
     uint32_t nOut;           // sequences written so far
 };
 
-struct LaneWalk {
-    uint32_t exit;           // cursor after the lane's segment
-    uint32_t cnt;            // matches taken
-    uint32_t merges;         // matches merged into their in-lane predecessor
-    uint32_t firstPos, firstOff;
-    uint32_t lastEnd, lastOff;
-};
-
-// Chases the jump links of the lane's segment (= one group) from `entry`.  In emit mode the matches
-// are also written: new sequences go to out[outIdx...]; a leading continuation of the previous
-// sequence is returned in `headAdd` (the caller adds it to out[firstIdx - 1].matchLength).
-template <bool kEmit>
-__device__ __forceinline__ void lane_walk(const uint32_t *links, uint32_t base, uint32_t group,
-                                          uint32_t entry, LaneWalk &r, uint32_t anchor, uint32_t prevOff,
-                                          uint4 *out, uint32_t outIdx, uint32_t &headAdd)
+// Emits the matches of the lane's segment (= one group) by chasing the jump links from `entry`.
+// New sequences go to out[outIdx...]; a leading continuation of the previous sequence is returned
+// (the caller adds it to out[firstIdx - 1].matchLength).
+__device__ __forceinline__ uint32_t lane_emit(const uint32_t *links, uint32_t base, uint32_t group, uint32_t entry,
+                                              uint32_t anchor, uint32_t prevOff, uint4 *out, uint32_t outIdx)
 {
     const uint32_t segStart = base + group * 32u, segEnd = segStart + 32u;
-    uint32_t c = entry;
-    r.cnt = 0; r.merges = 0; r.firstPos = 0; r.firstOff = 0; r.lastEnd = 0; r.lastOff = 0;
-    uint32_t openOff = 0, openLit = 0, openLen = 0;   // sequence being accumulated (emit mode)
+    uint32_t c = entry, headAdd = 0;
+    uint32_t openOff = 0, openLit = 0, openLen = 0;   // sequence being accumulated
     bool haveOpen = false;
-    headAdd = 0;
     while (c < segEnd) {
         const uint32_t w = links[ring_index(group, c - segStart)];
         const uint32_t tgt = base + (w & 0x7FFu);
         if (((w >> 11) & 3u) == kKindTake) {
-            const uint32_t o = w >> 13;
-            if (r.cnt == 0) { r.firstPos = c; r.firstOff = o; }
-            else if (c == r.lastEnd && o == r.lastOff) r.merges++;
-            r.cnt++;
-            if (kEmit) {
-                const uint32_t lit = c - anchor, len = tgt - c;
-                if (lit == 0 && o == prevOff && anchor > 0) {
-                    if (haveOpen) openLen += len; else headAdd += len;
-                } else {
-                    if (haveOpen) out[outIdx++] = make_uint4(openOff, openLit, openLen, 0u);
-                    openOff = o; openLit = lit; openLen = len; haveOpen = true;
-                }
-                anchor = tgt; prevOff = o;
+            const uint32_t o = w >> 13, lit = c - anchor, len = tgt - c;
+            if (lit == 0 && o == prevOff && anchor > 0) {
+                if (haveOpen) openLen += len; else headAdd += len;
+            } else {
+                if (haveOpen) out[outIdx++] = make_uint4(openOff, openLit, openLen, 0u);
+                openOff = o; openLit = lit; openLen = len; haveOpen = true;
             }
-            r.lastEnd = tgt; r.lastOff = o;
+            anchor = tgt; prevOff = o;
         }
         c = tgt;
     }
-    if (kEmit && haveOpen) out[outIdx] = make_uint4(openOff, openLit, openLen, 0u);
-    r.exit = c;
+    if (haveOpen) out[outIdx] = make_uint4(openOff, openLit, openLen, 0u);
+    return headAdd;
 }
 
 __device__ __forceinline__ void stage_parse(const Shared &S, uint32_t slot, uint32_t lane, uint32_t base,
                                             ParseCarry &pc, uint4 *out)
 {
     const uint32_t *links = S.ring0 + slot * kWindow;
-    const uint32_t segStart = base + lane * 32u;
+    const uint32_t *paths = S.ring1 + slot * kWindow;
+    const uint32_t segStart = base + lane * 32u, segEnd = segStart + 32u;
 
-    // ---- speculative parse, iterated until every lane's entry equals its predecessor's exit
-    LaneWalk w;
-    uint32_t dummy;
+    // ---- every lane guesses that the parser enters its segment at the segment start, then the
+    // guesses are corrected from lane 0 upward until nothing changes: each correction is one
+    // table look-up (the exit of the walk from any entry was tabulated by the J stage).
+    // A lane whose entry lies beyond its segment is passed over (a long match covers it); the
+    // entry of a lane is the exit of the nearest earlier lane that is NOT passed over, i.e. the
+    // prefix maximum over live lanes — so a run of covered lanes costs one round, not one each.
     uint32_t entry = lane == 0 ? max(pc.cursor, base) : segStart;
-    lane_walk<false>(links, base, lane, entry, w, 0, 0, nullptr, 0, dummy);
+    uint32_t path = 0, exitPos = 0;
     for (;;) {
-        const uint32_t prevExit = __shfl_up_sync(0xFFFFFFFFu, w.exit, 1);
-        const uint32_t want = lane == 0 ? entry : max(prevExit, segStart);
-        const bool changed = want != entry;
-        if (!__any_sync(0xFFFFFFFFu, changed)) break;
-        if (changed) {
-            entry = want;
-            lane_walk<false>(links, base, lane, entry, w, 0, 0, nullptr, 0, dummy);
+        const bool live = entry < segEnd;
+        path = live ? paths[ring_index(lane, entry - segStart)] : 0u;
+        exitPos = live ? segStart + (path & 0x1FFu) : 0u;          // passed-over lanes contribute nothing
+        uint32_t pm = lane == 0 ? max(exitPos, entry) : exitPos;   // lane 0 also carries the window's entry cursor
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pm, d);
+            if (lane >= static_cast<uint32_t>(d)) pm = max(pm, o);
         }
+        const uint32_t prevMax = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
+        const uint32_t want = lane == 0 ? entry : max(prevMax, segStart);
+        const bool changed = want != entry;
+        entry = want;
+        if (!__any_sync(0xFFFFFFFFu, changed)) { exitPos = pm; break; }   // pm: cursor after this lane's segment
+    }
+    const uint32_t cnt = (path >> 9) & 15u, merges = (path >> 13) & 15u;
+    uint32_t firstPos = 0, firstOff = 0, lastEnd = 0, lastOff = 0;
+    if (cnt) {
+        const uint32_t fl = (path >> 17) & 63u, ll = (path >> 23) & 63u;
+        const uint32_t wf = links[ring_index(lane, fl)], wl = links[ring_index(lane, ll)];
+        firstPos = segStart + fl; firstOff = wf >> 13;
+        lastEnd = base + (wl & 0x7FFu); lastOff = wl >> 13;
     }
 
     // ---- anchor / previous offset at each lane's entry: exclusive "last match" scan
-    uint32_t aE = w.cnt ? w.lastEnd : 0u, aO = w.lastOff;
+    uint32_t aE = cnt ? lastEnd : 0u, aO = lastOff;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t oe = __shfl_up_sync(0xFFFFFFFFu, aE, d);
@@ -426,8 +453,8 @@ __device__ __forceinline__ void stage_parse(const Shared &S, uint32_t slot, uint
     if (lane == 0 || anchor == 0) { anchor = pc.anchor; prevOff = pc.prevOff; }
 
     // ---- output slots
-    const bool headMerge = w.cnt && w.firstPos == anchor && w.firstOff == prevOff && anchor > 0;
-    const uint32_t fresh = w.cnt - w.merges - (headMerge ? 1u : 0u);
+    const bool headMerge = cnt && firstPos == anchor && firstOff == prevOff && anchor > 0;
+    const uint32_t fresh = cnt - merges - (headMerge ? 1u : 0u);
     uint32_t incl = fresh;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -438,15 +465,12 @@ __device__ __forceinline__ void stage_parse(const Shared &S, uint32_t slot, uint
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
 
     uint32_t headAdd = 0;
-    if (w.cnt) {
-        LaneWalk w2;
-        lane_walk<true>(links, base, lane, entry, w2, anchor, prevOff, out, firstIdx, headAdd);
-    }
+    if (cnt) headAdd = lane_emit(links, base, lane, entry, anchor, prevOff, out, firstIdx);
     __syncwarp();
     if (headAdd) atomicAdd(&out[firstIdx - 1].z, headAdd);   // continuation of an earlier lane's sequence
     __syncwarp();
 
-    pc.cursor = __shfl_sync(0xFFFFFFFFu, w.exit, 31);
+    pc.cursor = max(__shfl_sync(0xFFFFFFFFu, exitPos, 31), base + kWindow);
     if (totE) { pc.anchor = totE; pc.prevOff = totO; }
     pc.nOut += total;
 }
@@ -532,29 +556,33 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 const uint32_t need = min(bulk, (t + 1) * kWindow + 16u);
                 const uint32_t wantChunks = (need + kTmaChunk - 1) / kTmaChunk;
                 while (chunksSeen < wantChunks) { mbar_wait(smem_u32(&S.mbar[chunksSeen]), (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
-                // queue A: extension groups of window t-2 (heavier, first), then hash groups of window t
+                // One task queue per stage, heaviest first: extension groups of window t-2, their
+                // jump-link groups, then the hash groups of window t.  Jump task g only needs extension
+                // tasks g-8..g (a match is at most 256 bytes long), tracked in a completion bitmask, so
+                // it almost never waits; groups of the previous window were finished a stage ago.
                 const bool haveE = t >= 2 && t - 2 < nW;
                 const uint32_t nE = haveE ? kGroups : 0u;
-                const uint32_t nA = nE + (t < nW ? kGroups : 0u);
-                const uint32_t ctrA = smem_u32(&S.task[(t & 1u) * 2u]), ctrB = ctrA + 4u;
+                const uint32_t nH = t < nW ? kGroups : 0u;
+                const uint32_t nAll = 2u * nE + nH;
+                const uint32_t ctr = smem_u32(&S.task[(t & 1u) * 2u]);
+                volatile unsigned int *done = &S.task[(t & 1u) * 2u + 1u];
                 for (;;) {
-                    const uint32_t id = pop_task(ctrA, lane);
-                    if (id >= nA) break;
+                    const uint32_t id = pop_task(ctr, lane);
+                    if (id >= nAll) break;
                     if (id < nE) {
                         const uint32_t wdx = t - 2;
                         stage_extend(S, wdx & (kRing - 1), id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap);
-                    } else {
+                        __syncwarp();
+                        if (lane == 0) { __threadfence_block(); atomicOr(const_cast<unsigned int *>(done), 1u << id); }
+                    } else if (id < 2u * nE) {
                         const uint32_t g = id - nE;
+                        const uint32_t need = (g >= 8u ? 0x1FFu << (g - 8u) : (2u << g) - 1u);
+                        while ((*done & need) != need) __nanosleep(40);
+                        __threadfence_block();
+                        stage_jump(S, t - 2, g, lane, P.minMatch, P.lazyDepth);
+                    } else {
+                        const uint32_t g = id - 2u * nE;
                         stage_hash(S, t & (kRing - 1), g, lane, t * kWindow + g * 32u + lane, nh, P.shortMask);
-                    }
-                }
-                // all extension groups of window t-2 are done (hash/extend warps only): queue B, jump links
-                asm volatile("bar.sync 1, %0;" ::"n"(kEhWarps * 32) : "memory");
-                if (haveE) {
-                    for (;;) {
-                        const uint32_t id = pop_task(ctrB, lane);
-                        if (id >= kGroups) break;
-                        stage_jump(S, t - 2, id, lane, P.minMatch, P.lazyDepth);
                     }
                 }
             } else if (warp == kWarpTabL) {
