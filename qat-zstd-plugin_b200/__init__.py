@@ -32,7 +32,8 @@ __all__ = [
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqatseqprod.so")
+# B200SP_LIB lets a developer A/B-test another build of the same library; it is still the CUDA library.
+LIB_PATH = os.environ.get("B200SP_LIB") or os.path.join(_HERE, "libqatseqprod.so")
 
 BLOCK_MAX = 1 << 17
 SEQ_STRIDE = 43696
@@ -63,7 +64,7 @@ def _load():
         raise ImportError(
             f"{LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(or `make -C qat-zstd-plugin_b200/csrc`). There is no CPU fallback.")
-    l = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    l = ctypes.CDLL(LIB_PATH)
     # --- qatseqprod.h
     l.QZSTD_version.restype = c_char_p
     l.QZSTD_startQatDevice.restype = c_int

@@ -25,6 +25,10 @@
  */
 #include "lz77_kernels.cuh"
 
+#ifndef B200SP_SPIN_NS
+#define B200SP_SPIN_NS 100
+#endif
+
 namespace b200sp {
 
 // ------------------------------------------------------------------------------------------
@@ -569,19 +573,25 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 for (;;) {
                     const uint32_t id = pop_task(ctr, lane);
                     if (id >= nAll) break;
+#ifdef B200SP_ORDER_EHJ
+                    // order E, H, J
+                    const uint32_t jLo = nE + nH, hLo = nE;
+#else
+                    const uint32_t jLo = nE, hLo = 2u * nE;
+#endif
                     if (id < nE) {
                         const uint32_t wdx = t - 2;
                         stage_extend(S, wdx & (kRing - 1), id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap);
                         __syncwarp();
                         if (lane == 0) { __threadfence_block(); atomicOr(const_cast<unsigned int *>(done), 1u << id); }
-                    } else if (id < 2u * nE) {
-                        const uint32_t g = id - nE;
+                    } else if (id >= jLo && id < jLo + nE) {
+                        const uint32_t g = id - jLo;
                         const uint32_t need = (g >= 8u ? 0x1FFu << (g - 8u) : (2u << g) - 1u);
-                        while ((*done & need) != need) __nanosleep(40);
+                        while ((*done & need) != need) __nanosleep(B200SP_SPIN_NS);
                         __threadfence_block();
                         stage_jump(S, t - 2, g, lane, P.minMatch, P.lazyDepth);
                     } else {
-                        const uint32_t g = id - 2u * nE;
+                        const uint32_t g = id - hLo;
                         stage_hash(S, t & (kRing - 1), g, lane, t * kWindow + g * 32u + lane, nh, P.shortMask);
                     }
                 }

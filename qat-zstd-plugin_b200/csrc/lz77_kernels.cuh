@@ -24,7 +24,10 @@ constexpr uint32_t kInputPad      = 320;        // readable slack after the bloc
 constexpr uint32_t kTmaChunk      = 16384;
 constexpr uint32_t kTmaChunks     = kBlockMax / kTmaChunk;
 
-constexpr int kEhWarps   = 29;                  // hash + extension warps
+#ifndef B200SP_EH_WARPS
+#define B200SP_EH_WARPS 29
+#endif
+constexpr int kEhWarps   = B200SP_EH_WARPS;                  // hash + extension warps
 constexpr int kWarpTabL  = kEhWarps;            // serial owner of the long-hash table
 constexpr int kWarpTabS  = kEhWarps + 1;        // serial owner of the short-hash table
 constexpr int kWarpParse = kEhWarps + 2;        // speculative lane-parallel parser + emitter
