@@ -290,7 +290,7 @@ def main():
                    "level": args.level, "block_bytes": BLOCK, "blocks_per_gpu": n_blocks,
                    "cache": "input (212 MB) + sequence arrays exceed the 126 MB L2; no flush needed",
                    "corpus": info},
-        "sequences_per_step": n_seq, "gpu_launches": args.steps,
+        "sequences_per_step": n_seq * world, "gpu_launches": args.steps * world,
         "e2e": {"value": round(e2e, 3), "unit": "GB/s", "h2d_bytes_per_step": n_bytes, "d2h_bytes_per_step": d2h,
                 "steps": args.e2e_steps, "api": "b200sp_parse_host (pinned host input -> packed sequences on host)"},
         "roofline": roofline, "clocks": clocks,

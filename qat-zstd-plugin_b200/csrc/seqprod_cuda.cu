@@ -173,19 +173,25 @@ static cudaError_t grow_host(T *&ptr, size_t &cap, size_t want)
 }  // namespace
 
 // --------------------------------------------------------------------------------------------
+constexpr int kMaxChunks = 32;
+
 struct b200sp_engine {
     int device;
     int numSMs;
-    cudaStream_t stream;
+    cudaStream_t stream;         // compute
+    cudaStream_t sIn, sOut;      // host->device / device->host copies of the pipelined host path
+    cudaEvent_t evIn[kMaxChunks], evDone[kMaxChunks];
     unsigned int *d_work;        // dynamic scheduler counter
     // host-path scratch (grown on demand)
     uint8_t *d_src;      size_t d_srcCap;
     uint4 *d_seqs;       size_t d_seqsCap;      // entries
     uint32_t *d_counts;  size_t d_countsCap;
-    unsigned long long *d_offsets;
+    unsigned long long *d_offsets; size_t d_offsetsCap;
     unsigned long long *d_packed; size_t d_packedCap;   // entries
     uint8_t *h_stage;    size_t h_stageCap;     // pinned staging for pageable inputs
-    uint32_t *h_counts;  unsigned long long *h_offsets; size_t h_countsCap;
+    uint32_t *h_counts;  size_t h_countsCap;
+    unsigned long long *h_offsets; size_t h_offsetsCap;  // chunk-local (pinned)
+    unsigned long long *h_goffsets; size_t h_goffsetsCap; // global, handed to the caller
     unsigned long long *h_packed; size_t h_packedCap;
 };
 
@@ -229,6 +235,12 @@ int b200sp_engine_create(int device, b200sp_engine **out)
     cudaGetDeviceProperties(&prop, device);
     e->numSMs = prop.multiProcessorCount;
     ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->sIn, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->sOut, cudaStreamNonBlocking);
+    for (int k = 0; k < kMaxChunks && ce == cudaSuccess; k++) {
+        ce = cudaEventCreateWithFlags(&e->evIn[k], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->evDone[k], cudaEventDisableTiming);
+    }
     if (ce == cudaSuccess) ce = cudaMalloc(&e->d_work, 256);
     if (ce == cudaSuccess) ce = cudaMemset(e->d_work, 0, 256);
     if (ce != cudaSuccess) { b200sp_engine_destroy(e); return fail(B200SP_ECUDA, "engine_create", ce); }
@@ -241,6 +253,10 @@ void b200sp_engine_destroy(b200sp_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+    if (e->sIn) cudaStreamDestroy(e->sIn);
+    if (e->sOut) { cudaStreamSynchronize(e->sOut); cudaStreamDestroy(e->sOut); }
+    for (int k = 0; k < kMaxChunks; k++) { if (e->evIn[k]) cudaEventDestroy(e->evIn[k]); if (e->evDone[k]) cudaEventDestroy(e->evDone[k]); }
+    free(e->h_goffsets);
     cudaFree(e->d_work); cudaFree(e->d_src); cudaFree(e->d_seqs); cudaFree(e->d_counts);
     cudaFree(e->d_offsets); cudaFree(e->d_packed);
     cudaFreeHost(e->h_stage); cudaFreeHost(e->h_counts); cudaFreeHost(e->h_offsets); cudaFreeHost(e->h_packed);
@@ -349,75 +365,117 @@ int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint3
     const size_t nBlocks = (srcSize + blockSize - 1) / blockSize;
     if (nBlocks > 0x7FFFFFFFu) return fail(B200SP_EINVAL, "too many blocks");
     const size_t seqStride = (static_cast<size_t>(blockSize) / 4 + 2 + 7) & ~static_cast<size_t>(7);
+    const size_t perBlockWorst = static_cast<size_t>(blockSize) / 4 + 2;   // entries
     const size_t devBytes = nBlocks * stride + 16;
 
+    // ---- chunk plan: the copies of chunk k+1 / k-1 overlap the kernels of chunk k.  The first chunk
+    // is one wave of blocks (so the SMs start early), later chunks three waves (small launch tails).
+    const size_t sms = static_cast<size_t>(e->numSMs);
+    size_t big = 3 * sms;
+    if (nBlocks > sms + big * (kMaxChunks - 1)) big = ((nBlocks - sms + kMaxChunks - 2) / (kMaxChunks - 1) + sms - 1) / sms * sms;
+    size_t chunkStart[kMaxChunks + 1];
+    int nChunks = 0;
+    for (size_t b = 0; b < nBlocks;) {
+        chunkStart[nChunks++] = b;
+        b += (nChunks == 1 && nBlocks > sms) ? sms : big;
+    }
+    chunkStart[nChunks] = nBlocks;
+
     {
-        size_t cap = e->d_countsCap;
         CU_TRY(grow_dev(e->d_src, e->d_srcCap, devBytes), "cudaMalloc(src)");
         CU_TRY(grow_dev(e->d_seqs, e->d_seqsCap, nBlocks * seqStride), "cudaMalloc(seqs)");
         CU_TRY(grow_dev(e->d_counts, e->d_countsCap, nBlocks), "cudaMalloc(counts)");
-        if (e->d_countsCap != cap) {
-            cudaFree(e->d_offsets); e->d_offsets = nullptr;
-            CU_TRY(cudaMalloc(&e->d_offsets, (e->d_countsCap + 1) * sizeof(unsigned long long)), "cudaMalloc(offsets)");
-        }
-        size_t hc = e->h_countsCap;
+        CU_TRY(grow_dev(e->d_offsets, e->d_offsetsCap, nBlocks + kMaxChunks), "cudaMalloc(offsets)");
+        CU_TRY(grow_dev(e->d_packed, e->d_packedCap, nBlocks * perBlockWorst), "cudaMalloc(packed)");
         CU_TRY(grow_host(e->h_counts, e->h_countsCap, nBlocks), "cudaMallocHost(counts)");
-        if (e->h_countsCap != hc) {
-            cudaFreeHost(e->h_offsets); e->h_offsets = nullptr;
-            CU_TRY(cudaMallocHost(&e->h_offsets, (e->h_countsCap + 1) * sizeof(unsigned long long)), "cudaMallocHost(offsets)");
+        CU_TRY(grow_host(e->h_offsets, e->h_offsetsCap, nBlocks + kMaxChunks), "cudaMallocHost(offsets)");
+        if (e->h_goffsetsCap < nBlocks + 1) {
+            free(e->h_goffsets);
+            e->h_goffsets = static_cast<unsigned long long *>(malloc((nBlocks + 1 + nBlocks / 4) * sizeof(unsigned long long)));
+            if (!e->h_goffsets) { e->h_goffsetsCap = 0; return fail(B200SP_ENOMEM, "out of host memory"); }
+            e->h_goffsetsCap = nBlocks + 1 + nBlocks / 4;
         }
+        // typical text yields one entry per 10-20 input bytes; grown on demand below
+        CU_TRY(grow_host(e->h_packed, e->h_packedCap, srcSize / 12 + 4 * nBlocks + 1024), "cudaMallocHost(packed)");
     }
 
-    // ---- H2D.  Contiguous when the stride equals the block size (the common 128 KiB case).
     cudaPointerAttributes attr;
-    bool pinned = cudaPointerGetAttributes(&attr, h_src) == cudaSuccess &&
-                  (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+    const bool pinned = cudaPointerGetAttributes(&attr, h_src) == cudaSuccess &&
+                        (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
     (void)cudaGetLastError();
     const uint8_t *hs = static_cast<const uint8_t *>(h_src);
-    if (!pinned) {
-        // USDM-style staging (/root/reference/src/qatseqprod.c:1222-1224): memcpy into pinned memory
-        CU_TRY(grow_host(e->h_stage, e->h_stageCap, srcSize), "cudaMallocHost(stage)");
-        memcpy(e->h_stage, h_src, srcSize);
-        hs = e->h_stage;
-    }
-    if (stride == blockSize) {
-        CU_TRY(cudaMemcpyAsync(e->d_src, hs, srcSize, cudaMemcpyHostToDevice, e->stream), "H2D");
-    } else {
-        CU_TRY(cudaMemcpy2DAsync(e->d_src, stride, hs, blockSize, blockSize, srcSize / blockSize,
-                                 cudaMemcpyHostToDevice, e->stream), "H2D 2D");
-        const size_t rem = srcSize % blockSize;
-        if (rem) CU_TRY(cudaMemcpyAsync(e->d_src + (srcSize / blockSize) * stride, hs + (srcSize / blockSize) * blockSize,
-                                        rem, cudaMemcpyHostToDevice, e->stream), "H2D tail");
+    if (!pinned) CU_TRY(grow_host(e->h_stage, e->h_stageCap, srcSize), "cudaMallocHost(stage)");
+
+    // ---- enqueue: per chunk H2D on the copy-in stream, then parse + scan + pack + small D2H on the
+    // compute stream behind an event
+    for (int k = 0; k < nChunks; k++) {
+        const size_t b0 = chunkStart[k], b1 = chunkStart[k + 1], nb = b1 - b0;
+        const size_t byte0 = b0 * blockSize, byte1 = b1 * blockSize < srcSize ? b1 * blockSize : srcSize;
+        const uint8_t *hsrc = hs + byte0;
+        if (!pinned) {
+            // USDM-style staging (/root/reference/src/qatseqprod.c:1222-1224): memcpy into pinned memory
+            memcpy(e->h_stage + byte0, hs + byte0, byte1 - byte0);
+            hsrc = e->h_stage + byte0;
+        }
+        uint8_t *dsrc = e->d_src + b0 * stride;
+        if (stride == blockSize) {
+            CU_TRY(cudaMemcpyAsync(dsrc, hsrc, byte1 - byte0, cudaMemcpyHostToDevice, e->sIn), "H2D");
+        } else {
+            const size_t full = (byte1 - byte0) / blockSize, rem = (byte1 - byte0) % blockSize;
+            if (full) CU_TRY(cudaMemcpy2DAsync(dsrc, stride, hsrc, blockSize, blockSize, full, cudaMemcpyHostToDevice, e->sIn), "H2D 2D");
+            if (rem) CU_TRY(cudaMemcpyAsync(dsrc + full * stride, hsrc + full * blockSize, rem, cudaMemcpyHostToDevice, e->sIn), "H2D tail");
+        }
+        CU_TRY(cudaEventRecord(e->evIn[k], e->sIn), "event record");
+        CU_TRY(cudaStreamWaitEvent(e->stream, e->evIn[k], 0), "stream wait");
+
+        // sizes in the strided layout: the last block of the chunk holds what is left of the input
+        const uint64_t lastBytes = (byte1 - byte0) - (nb - 1) * static_cast<size_t>(blockSize);
+        const uint64_t totalStrided = (nb - 1) * stride + lastBytes;
+        uint4 *dseqs = e->d_seqs + b0 * seqStride;
+        uint32_t *dcounts = e->d_counts + b0;
+        unsigned long long *doffs = e->d_offsets + b0 + k;
+        int rc = b200sp_parse_device(e, dsrc, totalStrided, blockSize, stride, nullptr, static_cast<uint32_t>(nb), level,
+                                     reinterpret_cast<b200sp_sequence *>(dseqs), seqStride, dcounts, nullptr);
+        if (rc) return rc;
+        scan_counts_kernel<<<1, 1024, 0, e->stream>>>(dcounts, static_cast<uint32_t>(nb), doffs);
+        CU_TRY(cudaGetLastError(), "launch scan_counts_kernel");
+        pack_kernel<<<e->numSMs * 8, 256, 0, e->stream>>>(dseqs, seqStride, dcounts, doffs, static_cast<uint32_t>(nb),
+                                                         e->d_packed + b0 * perBlockWorst);
+        CU_TRY(cudaGetLastError(), "launch pack_kernel");
+        CU_TRY(cudaMemcpyAsync(e->h_counts + b0, dcounts, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream), "D2H counts");
+        CU_TRY(cudaMemcpyAsync(e->h_offsets + b0 + k, doffs, (nb + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream), "D2H offsets");
+        CU_TRY(cudaEventRecord(e->evDone[k], e->stream), "event record");
     }
 
-    // ---- parse + pack
-    // totalSize is expressed in the strided layout: the last block holds what is left of srcSize
-    const uint64_t lastBytes = srcSize - (nBlocks - 1) * static_cast<size_t>(blockSize);
-    const uint64_t totalStrided = (nBlocks - 1) * stride + lastBytes;
-    int rc = b200sp_parse_device(e, e->d_src, totalStrided, blockSize, stride, nullptr, static_cast<uint32_t>(nBlocks),
-                                 level, reinterpret_cast<b200sp_sequence *>(e->d_seqs), seqStride, e->d_counts, nullptr);
-    if (rc) return rc;
-    scan_counts_kernel<<<1, 1024, 0, e->stream>>>(e->d_counts, static_cast<uint32_t>(nBlocks), e->d_offsets);
-    CU_TRY(cudaGetLastError(), "launch scan_counts_kernel");
-    // worst case one entry per 4 input bytes plus one per block
-    const size_t packedWorst = srcSize / 4 + 2 * nBlocks;
-    CU_TRY(grow_dev(e->d_packed, e->d_packedCap, packedWorst), "cudaMalloc(packed)");
-    pack_kernel<<<e->numSMs * 8, 256, 0, e->stream>>>(e->d_seqs, seqStride, e->d_counts, e->d_offsets,
-                                                     static_cast<uint32_t>(nBlocks), e->d_packed);
-    CU_TRY(cudaGetLastError(), "launch pack_kernel");
-
-    // ---- D2H: sizes first, then exactly the packed entries
-    CU_TRY(cudaMemcpyAsync(e->h_counts, e->d_counts, nBlocks * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream), "D2H counts");
-    CU_TRY(cudaMemcpyAsync(e->h_offsets, e->d_offsets, (nBlocks + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream), "D2H offsets");
-    CU_TRY(cudaStreamSynchronize(e->stream), "sync after parse");
-    const size_t total = static_cast<size_t>(e->h_offsets[nBlocks]);
-    CU_TRY(grow_host(e->h_packed, e->h_packedCap, total), "cudaMallocHost(packed)");
-    CU_TRY(cudaMemcpyAsync(e->h_packed, e->d_packed, total * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream), "D2H packed");
-    CU_TRY(cudaStreamSynchronize(e->stream), "sync after D2H");
+    // ---- drain: as each chunk completes, fetch exactly its packed entries on the copy-out stream
+    size_t hostPos = 0;
+    for (int k = 0; k < nChunks; k++) {
+        const size_t b0 = chunkStart[k], nb = chunkStart[k + 1] - b0;
+        CU_TRY(cudaEventSynchronize(e->evDone[k]), "wait chunk");
+        const unsigned long long *lo = e->h_offsets + b0 + k;
+        const size_t total = static_cast<size_t>(lo[nb]);
+        if (hostPos + total > e->h_packedCap) {
+            // rare: denser than one entry per 12 bytes. Finish the copies in flight, move to a bigger buffer.
+            CU_TRY(cudaStreamSynchronize(e->sOut), "sync before grow");
+            unsigned long long *bigger = nullptr;
+            const size_t cap = (hostPos + total) * 2 + 1024;
+            CU_TRY(cudaMallocHost(&bigger, cap * sizeof(unsigned long long)), "cudaMallocHost(packed grow)");
+            memcpy(bigger, e->h_packed, hostPos * sizeof(unsigned long long));
+            cudaFreeHost(e->h_packed);
+            e->h_packed = bigger;
+            e->h_packedCap = cap;
+        }
+        CU_TRY(cudaMemcpyAsync(e->h_packed + hostPos, e->d_packed + b0 * perBlockWorst, total * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, e->sOut), "D2H packed");
+        for (size_t i = 0; i < nb; i++) e->h_goffsets[b0 + i] = hostPos + lo[i];
+        hostPos += total;
+    }
+    e->h_goffsets[nBlocks] = hostPos;
+    CU_TRY(cudaStreamSynchronize(e->sOut), "sync after D2H");
 
     res->nBlocks = static_cast<uint32_t>(nBlocks);
     res->counts = e->h_counts;
-    res->offsets = reinterpret_cast<const uint64_t *>(e->h_offsets);
+    res->offsets = reinterpret_cast<const uint64_t *>(e->h_goffsets);
     res->packed = reinterpret_cast<const uint64_t *>(e->h_packed);
     return B200SP_OK;
 }
