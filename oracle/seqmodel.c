@@ -78,26 +78,21 @@ static inline int32_t gain_of(uint32_t len, uint32_t off)
     return (int32_t)(len * 4u) - (int32_t)floorlog2(off + 1u);
 }
 
-size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t outCap,
-                      const SeqModelParams *prm)
+/* Steps 1-2 for every position: own best match (len 0 = none).  Shared by seqmodel_block and by the
+ * lane-level statement of the parse warps (lanemodel.c). */
+int seqmodel_own_matches(const uint8_t *src, size_t n, const SeqModelParams *prm, uint32_t *ownLen, uint32_t *ownOff)
 {
-    if (n > MODEL_MAX_BLOCK || outCap == 0) return (size_t)-1;
-
     const uint32_t N = (uint32_t)n;
     const uint32_t nh = N >= 8 ? N - 7 : 0;      /* positions that can hash 8 bytes */
     const size_t szL = (size_t)1 << prm->longBits, szS = (size_t)1 << prm->shortBits;
     uint16_t *tabL = (uint16_t *)malloc(szL * sizeof(uint16_t));
     uint16_t *tabS = (uint16_t *)malloc(szS * sizeof(uint16_t));
-    BestMatch *B = (BestMatch *)calloc(N + 1, sizeof(BestMatch));
-    if (!tabL || !tabS || !B) { free(tabL); free(tabS); free(B); return (size_t)-1; }
+    if (!tabL || !tabS) { free(tabL); free(tabS); return -1; }
     /* A slot keeps (position >> 1) of the most recent position with that hash: 16 bits cover the
      * whole 128 KiB block.  The dropped parity bit is recovered by testing both 2v and 2v+1.
      * 0xFFFF (positions 131070/131071, never hashable) is the empty marker. */
     memset(tabL, 0xFF, szL * sizeof(uint16_t));
     memset(tabS, 0xFF, szS * sizeof(uint16_t));
-
-    /* steps 1-3 fused: run-max of match ends carried left to right */
-    BestMatch run = {0, 0};
     for (uint32_t p = 0; p < N; p++) {
         uint32_t bestLen = 0, bestOff = 0;
         if (p < nh) {
@@ -134,9 +129,34 @@ size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t o
             }
             if (bestLen < (uint32_t)prm->minMatch) bestLen = 0;
         }
-        if (bestLen && p + bestLen > run.end) { run.end = p + bestLen; run.off = bestOff; }
+        ownLen[p] = bestLen;
+        ownOff[p] = bestOff;
+    }
+    free(tabL); free(tabS);
+    return 0;
+}
+
+size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t outCap,
+                      const SeqModelParams *prm)
+{
+    if (n > MODEL_MAX_BLOCK || outCap == 0) return (size_t)-1;
+
+    const uint32_t N = (uint32_t)n;
+    uint32_t *ownLen = (uint32_t *)malloc((N + 1) * sizeof(uint32_t));
+    uint32_t *ownOff = (uint32_t *)malloc((N + 1) * sizeof(uint32_t));
+    BestMatch *B = (BestMatch *)calloc(N + 1, sizeof(BestMatch));
+    if (!ownLen || !ownOff || !B || seqmodel_own_matches(src, n, prm, ownLen, ownOff) != 0) {
+        free(ownLen); free(ownOff); free(B);
+        return (size_t)-1;
+    }
+
+    /* step 3: run-max of match ends carried left to right */
+    BestMatch run = {0, 0};
+    for (uint32_t p = 0; p < N; p++) {
+        if (ownLen[p] && p + ownLen[p] > run.end) { run.end = p + ownLen[p]; run.off = ownOff[p]; }
         B[p] = run;                 /* strictly-greater replaces: ties keep the older match */
     }
+    free(ownLen); free(ownOff);
 
     /* step 4: parse */
     const uint32_t minMatch = (uint32_t)prm->minMatch;
@@ -182,6 +202,6 @@ size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t o
     out[nseq].rep = 0;
     nseq++;
 done:
-    free(tabL); free(tabS); free(B);
+    free(B);
     return nseq;
 }

@@ -44,6 +44,17 @@ void   seqmodel_params_for_level(int level, SeqModelParams *prm);
 size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t outCap,
                       const SeqModelParams *prm);
 
+/* Steps 1-2 of the model for every position p: ownLen[p] (0 = no match >= minMatch) and ownOff[p].
+ * Arrays hold n entries.  Returns 0, or -1 on allocation failure. */
+int    seqmodel_own_matches(const uint8_t *src, size_t n, const SeqModelParams *prm,
+                            uint32_t *ownLen, uint32_t *ownOff);
+
+/* Lane-level statement of the kernel's parse stage (lanemodel.c): same output as seqmodel_block, computed
+ * the way the parse warps compute it (per-group packed prefix maxima, carries, memoised per-group walks
+ * iterated to the serial fixed point, scans for anchors and output slots).  Test infrastructure. */
+size_t lanemodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t outCap,
+                       const SeqModelParams *prm);
+
 #if defined(__cplusplus)
 }
 #endif

@@ -11,17 +11,19 @@
  *   - the block is staged into shared memory with 1-D TMA bulk copies (UBLKCP), 16 KiB per
  *     mbarrier so the pipeline starts before the whole block has landed;
  *   - both hash tables (2 x 16 Ki x u16, positions stored >> 1) live in shared memory;
- *   - the block flows through a 4-deep ring of 1024-position windows, one role per stage:
- *       H  hash      16 warps   8-byte + short hash per position, intra-warp duplicate links
- *       T  table      2 warps   one warp per table walks the window in order: read slot,
+ *   - the block flows through rings of 1024-position windows, one role per stage time t:
+ *       H  hash     window t    28 warps (shared queue with E)  8-byte + short hash per position,
+ *                               intra-warp duplicate links resolved on the spot (match.any)
+ *       T  table    window t-1   2 warps  one warp per table walks the window in order: read slot,
  *                               overwrite with the newer position (exact serial semantics)
- *       E  extend    16 warps   probe the candidates (4-byte word compares), warp-cooperative
- *                               long extension, warp prefix-max of match ends
- *       P  parse      1 warp    lane-parallel speculative greedy/lazy parse (iterated to the
- *                               serial fixed point), sequence compaction, 16 B stores
- *     (the H and E roles share the same 16 warps).
- * The result is bit-identical to oracle/seqmodel.c, which is the serial statement of the same
- * four steps.  Integer/indexing work only: no tensor cores, no TMEM.
+ *       E  extend   window t-2  28 warps  probe both candidates on 16 bytes, warp-cooperative long
+ *                               extension, packed prefix maximum of match ends per 32-position group
+ *       P1 entries  window t-3   1 warp   lane = group: carry of the previous 8 groups, lazy decisions
+ *                               memoised as link words, group entries iterated to the serial fixed point
+ *       P2 emit     window t-4   1 warp   lane = group: follow the links, scans for anchors / output
+ *                               slots, 16-byte ZSTD_Sequence stores
+ * The result is bit-identical to oracle/seqmodel.c (the serial statement); oracle/lanemodel.c states
+ * the P1/P2 formulation lane by lane on the CPU.  Integer/indexing work only: no tensor cores, no TMEM.
  */
 #include "lz77_kernels.cuh"
 
@@ -77,18 +79,51 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// Unaligned little-endian 32-bit read from the staged block.
-__device__ __forceinline__ uint32_t ld32u(const uint32_t *in32, uint32_t bytePos)
+// Shared-memory accesses by 32-bit shared-window address.  All of the CTA's shared memory is one
+// dynamic array; its base is converted once (and made opaque, so ptxas keeps it in a register instead
+// of re-deriving it from SR_CgaCtaId at every access) and every structure is an offset from it.
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
 {
-    const uint32_t w = bytePos >> 2;
-    return __funnelshift_r(in32[w], in32[w + 1], (bytePos & 3u) * 8u);
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("{\n\t.reg .u16 t;\n\tld.shared.u16 t, [%1];\n\tcvt.u32.u16 %0, t;\n\t}" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v)
+{
+    asm volatile("{\n\t.reg .u16 t;\n\tcvt.u16.u32 t, %1;\n\tst.shared.u16 [%0], t;\n\t}" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v)
+{
+    asm volatile("{\n\t.reg .u16 t;\n\tcvt.u16.u32 t, %1;\n\tst.shared.u8 [%0], t;\n\t}" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(v) : "memory");
+}
+
+// Unaligned little-endian 32-bit read from the staged block (`in` = shared address of the block).
+__device__ __forceinline__ uint32_t ld32u(uint32_t in, uint32_t bytePos)
+{
+    const uint32_t a = in + (bytePos & ~3u);
+    return __funnelshift_r(lds32(a), lds32(a + 4u), (bytePos & 3u) * 8u);
 }
 
 // Warp-uniform pop from a shared-memory task counter: one ATOMS by lane 0, one broadcast.
 __device__ __forceinline__ uint32_t pop_task(uint32_t ctrAddr, uint32_t lane)
 {
     uint32_t id = 0;
-    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(id) : "r"(ctrAddr) : "memory");
+    // atom.inc (not .add): ptxas expands a predicated atom.add into a vote/popc aggregation sequence
+    if (lane == 0) asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(id) : "r"(ctrAddr) : "memory");
     return __shfl_sync(0xFFFFFFFFu, id, 0);
 }
 
@@ -96,35 +131,46 @@ __device__ __forceinline__ uint32_t ring_index(uint32_t group, uint32_t lane)
 {
     return group * 32u + (lane ^ group);   // XOR swizzle: conflict-free by group and by lane
 }
+__device__ __forceinline__ uint32_t ring_byte(uint32_t group, uint32_t lane)   // byte offset of a 32-bit ring word
+{
+    return (group * 32u + (lane ^ group)) * 4u;
+}
 
 __device__ __forceinline__ int32_t gain_of(uint32_t len, uint32_t off)
 {
     return static_cast<int32_t>(len * 4u) - static_cast<int32_t>(31 - __clz(off + 1u));
 }
 
-struct Shared {
-    uint32_t *in32;
-    uint16_t *tabL;
-    uint16_t *tabS;
-    uint32_t *ring0;    // [kRing][kWindow]
-    uint32_t *ring1;    // [kRing][kWindow]
-    uint32_t *gmax;     // [kRing][kGroups] packed farthest-reaching match of each group
-    uint64_t *mbar;     // [kTmaChunks]
-    volatile int *work; // next block index
-    unsigned int *task; // [2][2] per-stage task counters of the hash/extend warps (double-buffered)
+struct Shared {         // 32-bit shared-window addresses
+    uint32_t in;        // the staged block (+ pad)
+    uint32_t tabL;      // u16[1 << kLongBits]
+    uint32_t tabS;      // u16[1 << kShortBits]
+    uint32_t ringH;     // u32[2][kWindow]      H -> T: per table {hash:14 | linked:1 | last:1}, long in the low half
+    uint32_t ringC;     // u32[kRingC][kWindow] candidates {long u16 | short u16} (H, T) -> packed prefix maxima (E)
+    uint32_t ringL;     // u32[2][kWindow]      P1 -> P2: memoised decisions {end:9 | take lane:5 | offset:17}
+    uint32_t gmax;      // u32[kRingC][kGroups] packed farthest-reaching match of each group
+    uint32_t gown;      // u32[kRingC][kGroups] lanes whose own prefix maximum is a usable match
+    uint32_t hasA;      // u32[2][kGroups]      P1 -> P2: usable-match mask incl. the carry
+    uint32_t entA;      // u32[2][kGroups]      P1 -> P2: position at which the parse enters each group
+    uint32_t mbar;      // u64[kTmaChunks]
+    uint32_t work;      // next block index
+    uint32_t task;      // u32[2] per-stage task counters of the hash/extend warps (double-buffered)
 };
 
 // ------------------------------------------------------------------------------------------
-// H: hashes of one 32-position group -> ring words {hash | delta << 16 | last << 21 | valid << 22}
+// H: hashes of one 32-position group.  Lanes whose hash already occurred earlier in the group get
+// their candidate here (the nearest such lane); the others are left to the table warps.
+//   ringH word, per table: {hash:14 | linked:1 | last:1}   (invalid lanes: linked, not last)
+//   ringC word: {long candidate u16 | short candidate u16 << 16}, 0xFFFF = none / to be filled by T
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_hash(const Shared &S, uint32_t slot, uint32_t group, uint32_t lane,
+__device__ __forceinline__ void stage_hash(const Shared &S, uint32_t w, uint32_t group, uint32_t lane,
                                            uint32_t p, uint32_t nh, uint32_t shortMask)
 {
     const bool valid = p < nh;
     uint32_t hL = 0, hS = 0;
     if (valid) {
-        const uint32_t w = p >> 2, sh = (p & 3u) * 8u;
-        const uint32_t w0 = S.in32[w], w1 = S.in32[w + 1], w2 = S.in32[w + 2];
+        const uint32_t a = S.in + (p & ~3u), sh = (p & 3u) * 8u;
+        const uint32_t w0 = lds32(a), w1 = lds32(a + 4u), w2 = lds32(a + 8u);
         const uint32_t lo = __funnelshift_r(w0, w1, sh);
         const uint32_t hi = __funnelshift_r(w1, w2, sh);
         hL = (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> (32 - kLongBits);
@@ -136,52 +182,47 @@ __device__ __forceinline__ void stage_hash(const Shared &S, uint32_t slot, uint3
     const uint32_t mL = __match_any_sync(0xFFFFFFFFu, valid ? hL : (0x10000u | lane));
     const uint32_t mS = __match_any_sync(0xFFFFFFFFu, valid ? hS : (0x10000u | lane));
     const uint32_t bL = mL & ltMask, bS = mS & ltMask;
-    const uint32_t dL = bL ? lane - (31u - __clz(bL)) : 0u;   // distance to the nearest earlier lane with the same hash
-    const uint32_t dS = bS ? lane - (31u - __clz(bS)) : 0u;
-    const uint32_t lastL = (mL & geMask) == 0u, lastS = (mS & geMask) == 0u;
-    const uint32_t idx = slot * kWindow + ring_index(group, lane);
-    S.ring0[idx] = hL | (dL << 16) | (lastL << 21) | (static_cast<uint32_t>(valid) << 22);
-    S.ring1[idx] = hS | (dS << 16) | (lastS << 21) | (static_cast<uint32_t>(valid) << 22);
+    // nearest earlier lane with the same hash -> candidate position >> 1
+    const uint32_t cL = bL ? (p - lane + (31u - __clz(bL))) >> 1 : 0xFFFFu;
+    const uint32_t cS = bS ? (p - lane + (31u - __clz(bS))) >> 1 : 0xFFFFu;
+    const uint32_t linkedL = (bL != 0u) || !valid, linkedS = (bS != 0u) || !valid;
+    const uint32_t lastL = valid && (mL & geMask) == 0u, lastS = valid && (mS & geMask) == 0u;
+    const uint32_t ri = ring_byte(group, lane);
+    sts32(S.ringH + (w & 1u) * (kWindow * 4u) + ri, (hL | (linkedL << 14) | (lastL << 15)) | ((hS | (linkedS << 14) | (lastS << 15)) << 16));
+    sts32(S.ringC + (w & (kRingC - 1)) * (kWindow * 4u) + ri, cL | (cS << 16));
 }
 
 // ------------------------------------------------------------------------------------------
-// T: one warp walks one table over a window, group by group, in position order.
-// ring word in: hash/links from H; ring word out: candidate (position >> 1) or 0xFFFF.
+// T: one warp walks one table over a window, group by group, in position order, and fills the
+// candidates of the lanes H could not link inside their group.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_table(uint32_t *ring, uint16_t *tab, uint32_t slot, uint32_t lane,
-                                            uint32_t windowBase)
+__device__ __forceinline__ void stage_table(const Shared &S, uint32_t tab, uint32_t half, uint32_t w, uint32_t lane)
 {
-    uint32_t *r = ring + slot * kWindow;
+    const uint32_t rh = S.ringH + (w & 1u) * (kWindow * 4u);
+    const uint32_t rc = S.ringC + (w & (kRingC - 1)) * (kWindow * 4u) + half * 2u;
+    const uint32_t windowBase = w * kWindow, sh = half * 16u;
 #pragma unroll 1
     for (uint32_t g0 = 0; g0 < kGroups; g0 += 8) {
-        uint32_t w[8], tv[8];
+        uint32_t hw[8], tv[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) w[k] = r[ring_index(g0 + k, lane)];
+        for (int k = 0; k < 8; k++) hw[k] = (lds32(rh + ring_byte(g0 + k, lane)) >> sh) & 0xFFFFu;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const uint32_t h = w[k] & 0xFFFFu;
-            const bool valid = (w[k] >> 22) & 1u;
-            const bool last = (w[k] >> 21) & 1u;
+            const uint32_t ha = tab + (hw[k] & 0x3FFFu) * 2u;
             const uint32_t p = windowBase + (g0 + k) * 32u + lane;
-            tv[k] = tab[h];
-            if (valid && last) tab[h] = static_cast<uint16_t>(p >> 1);
+            tv[k] = lds16(ha);
+            if (hw[k] & 0x8000u) sts16(ha, p >> 1);
             __syncwarp();       // orders this group's stores before the next group's loads
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint32_t delta = (w[k] >> 16) & 31u;
-            const bool valid = (w[k] >> 22) & 1u;
-            const uint32_t p = windowBase + (g0 + k) * 32u + lane;
-            uint32_t cand = delta ? ((p - delta) >> 1) : tv[k];
-            if (!valid) cand = 0xFFFFu;
-            r[ring_index(g0 + k, lane)] = cand;
-        }
+        for (int k = 0; k < 8; k++)
+            if (!(hw[k] & 0x4000u)) sts16(rc + ring_byte(g0 + k, lane), tv[k]);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // E: candidates of one group -> best match per position -> prefix-max of match ends
-// ring out: ring0 = end (p + len, 0 if none so far in this group), ring1 = offset
+// ringC out: packed prefix maximum {end - groupStart:9 | 31 - lane:6 | offset:17} (0 = none so far)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t first_diff_16(uint32_t x1, uint32_t x2, uint32_t x3)
 {
@@ -194,13 +235,15 @@ __device__ __forceinline__ uint32_t first_diff_16(uint32_t x1, uint32_t x2, uint
     return len;
 }
 
-__device__ __forceinline__ void stage_extend(const Shared &S, uint32_t slot, uint32_t group, uint32_t lane,
+__device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32_t group, uint32_t lane,
                                              uint32_t p, uint32_t n, uint32_t nh, uint32_t minMatch,
                                              uint32_t extCap)
 {
-    const uint32_t idx = slot * kWindow + ring_index(group, lane);
-    const uint32_t cL = S.ring0[idx], cS = S.ring1[idx];
-    const uint32_t *in32 = S.in32;
+    const uint32_t slot = w & (kRingC - 1);
+    const uint32_t idx = S.ringC + slot * (kWindow * 4u) + ring_byte(group, lane);
+    const uint32_t cw = lds32(idx);
+    const uint32_t cL = cw & 0xFFFFu, cS = cw >> 16;
+    const uint32_t in = S.in;
     const bool valid = p < nh;
     uint32_t bestLen = 0, bestOff = 0;
     const uint32_t lim = valid ? min(n - p, extCap) : 0u;
@@ -208,8 +251,8 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t slot, uin
     // our own first 16 bytes, as four unaligned words (reads stay inside the padded buffer)
     uint32_t a0, a1, a2, a3;
     {
-        const uint32_t w = min(p, kBlockMax) >> 2, sh = (p & 3u) * 8u;
-        const uint32_t x0 = in32[w], x1 = in32[w + 1], x2 = in32[w + 2], x3 = in32[w + 3], x4 = in32[w + 4];
+        const uint32_t a = in + (min(p, kBlockMax) & ~3u), sh = (p & 3u) * 8u;
+        const uint32_t x0 = lds32(a), x1 = lds32(a + 4u), x2 = lds32(a + 8u), x3 = lds32(a + 12u), x4 = lds32(a + 16u);
         a0 = __funnelshift_r(x0, x1, sh); a1 = __funnelshift_r(x1, x2, sh);
         a2 = __funnelshift_r(x2, x3, sh); a3 = __funnelshift_r(x3, x4, sh);
     }
@@ -219,8 +262,8 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t slot, uin
         // the slot stands for positions 2c and 2c+1 (same 32-bit word row): pick the one whose first
         // 4 bytes equal ours, the nearer one if both do.  0xFFFF (empty) fails q0 < p by construction.
         const uint32_t q0 = 2u * c;
-        const uint32_t w = min(q0, kBlockMax) >> 2, sh0 = (q0 & 3u) * 8u;       // q0 even: sh0 is 0 or 16
-        const uint32_t y0 = in32[w], y1 = in32[w + 1], y2 = in32[w + 2], y3 = in32[w + 3], y4 = in32[w + 4];
+        const uint32_t a = in + (min(q0, kBlockMax) & ~3u), sh0 = (q0 & 3u) * 8u;   // q0 even: sh0 is 0 or 16
+        const uint32_t y0 = lds32(a), y1 = lds32(a + 4u), y2 = lds32(a + 8u), y3 = lds32(a + 12u), y4 = lds32(a + 16u);
         const bool c0 = valid && q0 < p && __funnelshift_r(y0, y1, sh0) == a0;
         const bool c1 = valid && q0 + 1u < p && __funnelshift_r(y0, y1, sh0 + 8u) == a0;
         const uint32_t sh = sh0 + (c1 ? 8u : 0u);
@@ -252,7 +295,7 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t slot, uin
         for (uint32_t k0 = kProbe; k0 < reach; k0 += 128u) {
             const uint32_t k = k0 + lane * 4u;
             uint32_t x = 0;
-            if (k < reach) x = ld32u(in32, ph + k) ^ ld32u(in32, qh + k);
+            if (k < reach) x = ld32u(in, ph + k) ^ ld32u(in, qh + k);
             const uint32_t bad = __ballot_sync(0xFFFFFFFFu, x != 0u);
             if (bad) {
                 const uint32_t l = __ffs(bad) - 1;
@@ -272,158 +315,100 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t slot, uin
         const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pk, d);
         if (lane >= static_cast<uint32_t>(d)) pk = max(pk, o);
     }
-    S.ring0[idx] = pk;                                   // prefix-max within the group
-    if (lane == 31) S.gmax[slot * kGroups + group] = pk; // the group's total, for the carry of later groups
+    sts32(idx, pk);                                      // prefix-max within the group
+    const uint32_t own = __ballot_sync(0xFFFFFFFFu, (pk >> 23) >= lane + minMatch);
+    if (lane == 31) { sts32(S.gmax + (slot * kGroups + group) * 4u, pk); sts32(S.gown + (slot * kGroups + group) * 4u, own); }
 }
 
 // ------------------------------------------------------------------------------------------
-// J: jump links of one group.  Folds the carry of the previous 8 groups (a match is at most
-// extCap = 256 bytes long, so nothing older can reach in) into the group's prefix-max, applies the
-// lazy rule, and leaves one word per position: {target - windowBase (11 bits), kind (2), offset (17)}.
-//   SKIP  no usable match here: go to the next position of the group that has one (or to its end)
-//   HOP   a later start is better (lazy): go to p+1 / p+2
-//   TAKE  emit the match [p, target) at `offset`
+// P1: where the serial parse enters every group of one window (lane j = group j).
+// oracle/lanemodel.c is the lane-by-lane CPU statement of this function and of stage_emit.
 // ------------------------------------------------------------------------------------------
-constexpr uint32_t kKindSkip = 0, kKindHop = 1, kKindTake = 2;
-
-__device__ __forceinline__ void stage_jump(const Shared &S, uint32_t wdx, uint32_t group, uint32_t lane,
-                                           uint32_t minMatch, uint32_t lazyDepth)
+__device__ __forceinline__ int32_t gain_packed(uint32_t b, uint32_t lane)
 {
-    const uint32_t slot = wdx & (kRing - 1);
-    const uint32_t idx = slot * kWindow + ring_index(group, lane);
-    // ---- carry: lane k-1 looks k groups back (possibly into the previous window's slot)
+    return static_cast<int32_t>(((b >> 23) - lane) * 4u) - static_cast<int32_t>(31 - __clz((b & 0x1FFFFu) + 1u));
+}
+
+// One decision: the cursor stands on local position p0 (a usable match starts there).  Applies the lazy
+// rule (look-ahead never leaves the group) and returns the link word {end:9 | take lane:5 | offset:17}.
+__device__ __forceinline__ uint32_t eval_take(uint32_t pkRow, uint32_t group, uint32_t p0, uint32_t c,
+                                              uint32_t has, uint32_t lazyDepth)
+{
+    uint32_t p = p0;
+    for (;;) {
+        const uint32_t b0 = max(lds32(pkRow + ring_byte(group, p)), c);
+        if (lazyDepth >= 1u) {
+            const int32_t g0 = gain_packed(b0, p);
+            const uint32_t q1 = p + 1u, q2 = p + 2u;
+            if (q1 < 32u && ((has >> q1) & 1u)) {
+                const uint32_t b1 = max(lds32(pkRow + ring_byte(group, q1)), c);
+                if (gain_packed(b1, q1) > g0 + 4) { p = q1; continue; }
+                if (lazyDepth >= 2u && q2 < 32u && ((has >> q2) & 1u)) {
+                    const uint32_t b2 = max(lds32(pkRow + ring_byte(group, q2)), c);
+                    if (gain_packed(b2, q2) > g0 + 7) { p = q2; continue; }
+                }
+            }
+        }
+        return ((b0 >> 23) << 22) | (p << 17) | (b0 & 0x1FFFFu);
+    }
+}
+
+__device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint32_t lane, uint32_t &cursor,
+                                              uint32_t minMatch, uint32_t lazyDepth)
+{
+    const uint32_t slot = w & (kRingC - 1), base = w * kWindow;
+    const uint32_t pkRow = S.ringC + slot * (kWindow * 4u);
+    const uint32_t linkRow = S.ringL + (w & 1u) * (kWindow * 4u);
+    // ---- carry: farthest-reaching match of the previous 8 groups (a match is at most extCap = 256
+    // bytes long, so nothing older can reach in), re-based to this group; it wins ties (it is older)
     uint32_t c = 0;
-    if (lane < 8) {
-        const uint32_t k = lane + 1;
-        int gg = static_cast<int>(group) - static_cast<int>(k);
+#pragma unroll
+    for (uint32_t k = 1; k <= 8; k++) {
+        int gg = static_cast<int>(lane) - static_cast<int>(k);
         uint32_t sl = slot;
         bool ok = true;
-        if (gg < 0) { ok = wdx > 0; gg += kGroups; sl = (wdx - 1) & (kRing - 1); }
-        if (ok) {
-            const uint32_t v = S.gmax[sl * kGroups + gg];
-            const uint32_t rel = v >> 23;
-            if (rel > 32u * k) c = ((rel - 32u * k) << 23) | ((32u + k) << 17) | (v & 0x1FFFFu);
-        }
+        if (gg < 0) { ok = w > 0; gg += kGroups; sl = (w - 1) & (kRingC - 1); }
+        const uint32_t v = ok ? lds32(S.gmax + (sl * kGroups + gg) * 4u) : 0u;
+        const uint32_t rel = v >> 23;
+        if (rel > 32u * k) c = max(c, ((rel - 32u * k) << 23) | ((32u + k) << 17) | (v & 0x1FFFFu));
     }
-    c = __reduce_max_sync(0xFFFFFFFFu, c);
-    const uint32_t bt = max(S.ring0[idx], c);              // B(p): farthest-reaching match covering p
-    const uint32_t rel = bt >> 23, off = bt & 0x1FFFFu;
-    const bool has = rel >= lane + minMatch;
-    const int32_t gain = static_cast<int32_t>((rel - lane) * 4u) - static_cast<int32_t>(31 - __clz(off + 1u));
-
-    // ---- B(p+1), B(p+2) by shuffle.  The look-ahead never leaves the group (model: window = 32).
-    const uint32_t b1 = __shfl_down_sync(0xFFFFFFFFu, bt, 1), b2 = __shfl_down_sync(0xFFFFFFFFu, bt, 2);
-    const uint32_t l1 = lane + 1, l2 = lane + 2;
-    const bool ok1 = lane < 31 && (b1 >> 23) >= l1 + minMatch;
-    const bool ok2 = lane < 30 && (b2 >> 23) >= l2 + minMatch;
-    const int32_t gain1 = static_cast<int32_t>(((b1 >> 23) - l1) * 4u) - static_cast<int32_t>(31 - __clz((b1 & 0x1FFFFu) + 1u));
-    const int32_t gain2 = static_cast<int32_t>(((b2 >> 23) - l2) * 4u) - static_cast<int32_t>(31 - __clz((b2 & 0x1FFFFu) + 1u));
-    uint32_t adv = 0;
-    if (has && lazyDepth >= 1 && ok1) {
-        if (gain1 > gain + 4) adv = 1;
-        else if (lazyDepth >= 2 && ok2 && gain2 > gain + 7) adv = 2;
-    }
-    const uint32_t hasMask = __ballot_sync(0xFFFFFFFFu, has);
-    const uint32_t groupRel = group * 32u;                  // group start relative to the window
-    uint32_t tgt, kind;
-    if (has) {
-        kind = adv ? kKindHop : kKindTake;
-        tgt = groupRel + (adv ? lane + adv : rel);
-    } else {
-        const uint32_t m = hasMask & ~((2u << lane) - 1u);
-        kind = kKindSkip;
-        tgt = groupRel + (m ? __ffs(m) - 1 : 32u);
-    }
-    S.ring0[idx] = tgt | (kind << 11) | (off << 13);
-
-    // ---- path summaries by pointer doubling.  For a cursor standing on this position: where the
-    // walk leaves the group, how many matches it takes, how many of them absorb their successor
-    // (zero literals, same offset), and which lanes hold the first / last taken match.
-    //   word = next (9 bits, >= 32: left the group, relative to the group start) | taken (4) |
-    //          absorbed (4) | first lane (6, 32 = none) | last lane (6, 32 = none)
-    const uint32_t nxt = tgt - groupRel;                              // 1 .. 32 + 256
-    const bool take = kind == kKindTake;
-    uint32_t absorb = 0;
-    {
-        const uint32_t succ = __shfl_sync(0xFFFFFFFFu, S.ring0[idx], nxt & 31u);   // link word of the node at our target
-        absorb = take && nxt < 32u && ((succ >> 11) & 3u) == kKindTake && (succ >> 13) == off;
-    }
-    uint32_t pk = nxt | ((take ? 1u : 0u) << 9) | (absorb << 13) | ((take ? lane : 32u) << 17) | ((take ? lane : 32u) << 23);
-#pragma unroll 1
-    for (int round = 0; round < 5; round++) {
-        const uint32_t cur = pk & 0x1FFu;
-        if (__all_sync(0xFFFFFFFFu, cur >= 32u)) break;
-        const uint32_t o = __shfl_sync(0xFFFFFFFFu, pk, cur & 31u);
-        if (cur < 32u) {
-            const uint32_t ft = (pk >> 17) & 63u, olt = (o >> 23) & 63u;
-            const uint32_t nft = ft < 32u ? ft : (o >> 17) & 63u;
-            const uint32_t nlt = olt < 32u ? olt : (pk >> 23) & 63u;
-            const uint32_t cnts = ((pk >> 9) & 0xFFu) + ((o >> 9) & 0xFFu);   // taken | absorbed << 4, no carry: <= 8 each
-            pk = (o & 0x1FFu) | (cnts << 9) | (nft << 17) | (nlt << 23);
-        }
-    }
-    S.ring1[idx] = pk;
-}
-
-// ------------------------------------------------------------------------------------------
-// P: parse one window.  Lane j owns positions [base + 32 j, base + 32 j + 32).
-// ------------------------------------------------------------------------------------------
-struct ParseCarry {          // uniform across the warp, carried from window to window
-    uint32_t cursor;         // first position the parser has not consumed yet
-    uint32_t anchor;         // end of the last emitted match
-    uint32_t prevOff;        // offset of the last emitted match
-    uint32_t nOut;           // sequences written so far
-};
-
-// Emits the matches of the lane's segment (= one group) by chasing the jump links from `entry`.
-// New sequences go to out[outIdx...]; a leading continuation of the previous sequence is returned
-// (the caller adds it to out[firstIdx - 1].matchLength).
-__device__ __forceinline__ uint32_t lane_emit(const uint32_t *links, uint32_t base, uint32_t group, uint32_t entry,
-                                              uint32_t anchor, uint32_t prevOff, uint4 *out, uint32_t outIdx)
-{
-    const uint32_t segStart = base + group * 32u, segEnd = segStart + 32u;
-    uint32_t c = entry, headAdd = 0;
-    uint32_t openOff = 0, openLit = 0, openLen = 0;   // sequence being accumulated
-    bool haveOpen = false;
-    while (c < segEnd) {
-        const uint32_t w = links[ring_index(group, c - segStart)];
-        const uint32_t tgt = base + (w & 0x7FFu);
-        if (((w >> 11) & 3u) == kKindTake) {
-            const uint32_t o = w >> 13, lit = c - anchor, len = tgt - c;
-            if (lit == 0 && o == prevOff && anchor > 0) {
-                if (haveOpen) openLen += len; else headAdd += len;
-            } else {
-                if (haveOpen) out[outIdx++] = make_uint4(openOff, openLit, openLen, 0u);
-                openOff = o; openLit = lit; openLen = len; haveOpen = true;
-            }
-            anchor = tgt; prevOff = o;
-        }
-        c = tgt;
-    }
-    if (haveOpen) out[outIdx] = make_uint4(openOff, openLit, openLen, 0u);
-    return headAdd;
-}
-
-__device__ __forceinline__ void stage_parse(const Shared &S, uint32_t slot, uint32_t lane, uint32_t base,
-                                            ParseCarry &pc, uint4 *out)
-{
-    const uint32_t *links = S.ring0 + slot * kWindow;
-    const uint32_t *paths = S.ring1 + slot * kWindow;
+    const uint32_t cRel = c >> 23;
+    uint32_t cover = 0;
+    if (cRel >= minMatch) cover = (cRel - minMatch >= 31u) ? 0xFFFFFFFFu : (2u << (cRel - minMatch)) - 1u;
+    const uint32_t has = lds32(S.gown + (slot * kGroups + lane) * 4u) | cover;
     const uint32_t segStart = base + lane * 32u, segEnd = segStart + 32u;
 
-    // ---- every lane guesses that the parser enters its segment at the segment start, then the
-    // guesses are corrected from lane 0 upward until nothing changes: each correction is one
-    // table look-up (the exit of the walk from any entry was tabulated by the J stage).
-    // A lane whose entry lies beyond its segment is passed over (a long match covers it); the
-    // entry of a lane is the exit of the nearest earlier lane that is NOT passed over, i.e. the
-    // prefix maximum over live lanes — so a run of covered lanes costs one round, not one each.
-    uint32_t entry = lane == 0 ? max(pc.cursor, base) : segStart;
-    uint32_t path = 0, exitPos = 0;
+    // ---- every lane guesses that the parser enters its group at its first position; the guesses are
+    // corrected from lane 0 upward until nothing changes.  A lane whose entry lies beyond its group is
+    // passed over (a long match covers it): the entry of a lane is the exit of the nearest earlier lane
+    // that is NOT passed over, i.e. the prefix maximum over live lanes.  A walk depends only on where it
+    // starts, and every decision is memoised, so a corrected lane re-evaluates nothing it has seen.
+    // First guess: the parse arrives through the carried match (the farthest-reaching one usually is the
+    // one the previous groups ended with); any guess converges to the same fixed point.
+    uint32_t entry = lane == 0 ? max(cursor, base) : segStart + min(cRel, 32u);
+    uint32_t visited = 0, pm = 0, walked = 0xFFFFFFFFu, exitPos = 0;
     for (;;) {
-        const bool live = entry < segEnd;
-        path = live ? paths[ring_index(lane, entry - segStart)] : 0u;
-        exitPos = live ? segStart + (path & 0x1FFu) : 0u;          // passed-over lanes contribute nothing
-        uint32_t pm = lane == 0 ? max(exitPos, entry) : exitPos;   // lane 0 also carries the window's entry cursor
+        if (entry != walked) {                   // a lane whose entry did not change keeps its exit
+            walked = entry;
+            const bool live = entry < segEnd;
+            uint32_t cur = live ? entry - segStart : 32u;
+            while (cur < 32u) {
+                const uint32_t m = has & (0xFFFFFFFFu << cur);
+                if (!m) { cur = 32u; break; }
+                const uint32_t p0 = __ffs(m) - 1;
+                uint32_t L;
+                if ((visited >> p0) & 1u) L = lds32(linkRow + ring_byte(lane, p0));
+                else {
+                    L = eval_take(pkRow, lane, p0, c, has, lazyDepth);
+                    sts32(linkRow + ring_byte(lane, p0), L);
+                    visited |= 1u << p0;
+                }
+                cur = L >> 22;
+            }
+            exitPos = live ? segStart + cur : 0u;                    // passed-over lanes contribute nothing
+        }
+        __syncwarp();
+        pm = lane == 0 ? max(exitPos, entry) : exitPos;              // lane 0 also carries the window's entry cursor
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pm, d);
@@ -433,16 +418,47 @@ __device__ __forceinline__ void stage_parse(const Shared &S, uint32_t slot, uint
         const uint32_t want = lane == 0 ? entry : max(prevMax, segStart);
         const bool changed = want != entry;
         entry = want;
-        if (!__any_sync(0xFFFFFFFFu, changed)) { exitPos = pm; break; }   // pm: cursor after this lane's segment
+        if (!__any_sync(0xFFFFFFFFu, changed)) break;
     }
-    const uint32_t cnt = (path >> 9) & 15u, merges = (path >> 13) & 15u;
-    uint32_t firstPos = 0, firstOff = 0, lastEnd = 0, lastOff = 0;
-    if (cnt) {
-        const uint32_t fl = (path >> 17) & 63u, ll = (path >> 23) & 63u;
-        const uint32_t wf = links[ring_index(lane, fl)], wl = links[ring_index(lane, ll)];
-        firstPos = segStart + fl; firstOff = wf >> 13;
-        lastEnd = base + (wl & 0x7FFu); lastOff = wl >> 13;
+    cursor = max(__shfl_sync(0xFFFFFFFFu, pm, 31), base + kWindow);
+    sts32(S.hasA + ((w & 1u) * kGroups + lane) * 4u, has);
+    sts32(S.entA + ((w & 1u) * kGroups + lane) * 4u, entry);
+}
+
+// ------------------------------------------------------------------------------------------
+// P2: emit one window.  Lane j owns positions [base + 32 j, base + 32 j + 32).
+// ------------------------------------------------------------------------------------------
+struct EmitCarry {           // uniform across the warp, carried from window to window
+    uint32_t anchor;         // end of the last emitted match
+    uint32_t prevOff;        // offset of the last emitted match
+    uint32_t nOut;           // sequences written so far
+};
+
+__device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t lane, EmitCarry &ec, uint4 *out)
+{
+    const uint32_t base = w * kWindow;
+    const uint32_t linkRow = S.ringL + (w & 1u) * (kWindow * 4u);
+    const uint32_t has = lds32(S.hasA + ((w & 1u) * kGroups + lane) * 4u);
+    const uint32_t entry = lds32(S.entA + ((w & 1u) * kGroups + lane) * 4u);
+    const uint32_t segStart = base + lane * 32u, segEnd = segStart + 32u;
+    const uint32_t cur0 = entry < segEnd ? entry - segStart : 32u;
+
+    // ---- counting walk along the memoised links
+    uint32_t cnt = 0, merges = 0, firstPos = 0, firstOff = 0, lastEnd = 0, lastOff = 0;
+    {
+        uint32_t cur = cur0;
+        while (cur < 32u) {
+            const uint32_t m = has & (0xFFFFFFFFu << cur);
+            if (!m) break;
+            const uint32_t L = lds32(linkRow + ring_byte(lane, __ffs(m) - 1));
+            const uint32_t p = segStart + ((L >> 17) & 31u), end = segStart + (L >> 22), off = L & 0x1FFFFu;
+            if (cnt && p == lastEnd && off == lastOff) merges++;
+            if (!cnt) { firstPos = p; firstOff = off; }
+            cnt++; lastEnd = end; lastOff = off;
+            cur = L >> 22;
+        }
     }
+    __syncwarp();
 
     // ---- anchor / previous offset at each lane's entry: exclusive "last match" scan
     uint32_t aE = cnt ? lastEnd : 0u, aO = lastOff;
@@ -454,7 +470,7 @@ __device__ __forceinline__ void stage_parse(const Shared &S, uint32_t slot, uint
     }
     const uint32_t totE = __shfl_sync(0xFFFFFFFFu, aE, 31), totO = __shfl_sync(0xFFFFFFFFu, aO, 31);
     uint32_t anchor = __shfl_up_sync(0xFFFFFFFFu, aE, 1), prevOff = __shfl_up_sync(0xFFFFFFFFu, aO, 1);
-    if (lane == 0 || anchor == 0) { anchor = pc.anchor; prevOff = pc.prevOff; }
+    if (lane == 0 || anchor == 0) { anchor = ec.anchor; prevOff = ec.prevOff; }
 
     // ---- output slots
     const bool headMerge = cnt && firstPos == anchor && firstOff == prevOff && anchor > 0;
@@ -465,18 +481,39 @@ __device__ __forceinline__ void stage_parse(const Shared &S, uint32_t slot, uint
         const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
         if (lane >= static_cast<uint32_t>(d)) incl += v;
     }
-    const uint32_t firstIdx = pc.nOut + incl - fresh;
+    const uint32_t firstIdx = ec.nOut + incl - fresh;
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
 
+    // ---- emitting walk.  New sequences go to out[firstIdx...]; a leading continuation of an earlier
+    // lane's sequence is added to out[firstIdx - 1].matchLength afterwards.
     uint32_t headAdd = 0;
-    if (cnt) headAdd = lane_emit(links, base, lane, entry, anchor, prevOff, out, firstIdx);
+    if (cnt) {
+        uint32_t cur = cur0, outIdx = firstIdx;
+        uint32_t openOff = 0, openLit = 0, openLen = 0;   // sequence being accumulated
+        bool haveOpen = false;
+        while (cur < 32u) {
+            const uint32_t m = has & (0xFFFFFFFFu << cur);
+            if (!m) break;
+            const uint32_t L = lds32(linkRow + ring_byte(lane, __ffs(m) - 1));
+            const uint32_t p = segStart + ((L >> 17) & 31u), end = segStart + (L >> 22), o = L & 0x1FFFFu;
+            const uint32_t lit = p - anchor, len = end - p;
+            if (lit == 0 && o == prevOff && anchor > 0) {
+                if (haveOpen) openLen += len; else headAdd += len;
+            } else {
+                if (haveOpen) out[outIdx++] = make_uint4(openOff, openLit, openLen, 0u);
+                openOff = o; openLit = lit; openLen = len; haveOpen = true;
+            }
+            anchor = end; prevOff = o;
+            cur = L >> 22;
+        }
+        if (haveOpen) out[outIdx] = make_uint4(openOff, openLit, openLen, 0u);
+    }
     __syncwarp();
     if (headAdd) atomicAdd(&out[firstIdx - 1].z, headAdd);   // continuation of an earlier lane's sequence
     __syncwarp();
 
-    pc.cursor = max(__shfl_sync(0xFFFFFFFFu, exitPos, 31), base + kWindow);
-    if (totE) { pc.anchor = totE; pc.prevOff = totO; }
-    pc.nOut += total;
+    if (totE) { ec.anchor = totE; ec.prevOff = totO; }
+    ec.nOut += total;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -487,30 +524,35 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
     extern __shared__ __align__(128) uint8_t smem[];
     Shared S;
     {
-        uint8_t *p = smem;
-        S.in32 = reinterpret_cast<uint32_t *>(p);  p += kSmemInput;
-        S.tabL = reinterpret_cast<uint16_t *>(p);  p += kSmemTabL;
-        S.tabS = reinterpret_cast<uint16_t *>(p);  p += kSmemTabS;
-        S.ring0 = reinterpret_cast<uint32_t *>(p); p += kSmemRing / 2;
-        S.ring1 = reinterpret_cast<uint32_t *>(p); p += kSmemRing / 2;
-        S.gmax = reinterpret_cast<uint32_t *>(p);  p += kSmemGmax;
-        S.mbar = reinterpret_cast<uint64_t *>(p);  p += kTmaChunks * 8;
-        S.work = reinterpret_cast<volatile int *>(p);  p += 8;
-        S.task = reinterpret_cast<unsigned int *>(p);
+        uint32_t p;
+        asm volatile("mov.u32 %0, %1;" : "=r"(p) : "r"(smem_u32(smem)));   // opaque: one register, never re-derived
+        S.in = p;    p += kSmemInput;
+        S.tabL = p;  p += kSmemTabL;
+        S.tabS = p;  p += kSmemTabS;
+        S.ringH = p; p += kSmemRingH;
+        S.ringC = p; p += kSmemRingC;
+        S.ringL = p; p += kSmemRingL;
+        S.gmax = p;  p += kRingC * kGroups * 4;
+        S.gown = p;  p += kRingC * kGroups * 4;
+        S.hasA = p;  p += 2 * kGroups * 4;
+        S.entA = p;  p += 2 * kGroups * 4;
+        S.mbar = p;  p += kTmaChunks * 8;
+        S.work = p;  p += 8;
+        S.task = p;
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     if (tid == 0) {
-        for (uint32_t c = 0; c < kTmaChunks; c++) mbar_init(smem_u32(&S.mbar[c]), 1);
+        for (uint32_t c = 0; c < kTmaChunks; c++) mbar_init(S.mbar + c * 8u, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     uint32_t tmaParity = 0;            // bit c = phase parity mbarrier c completes next
 
     for (;;) {
         __syncthreads();                       // previous block fully retired; mbarriers initialised
-        if (tid == 0) *S.work = static_cast<int>(atomicAdd(P.workCounter, 1u));
+        if (tid == 0) sts32(S.work, atomicAdd(P.workCounter, 1u));
         __syncthreads();
-        const uint32_t b = static_cast<uint32_t>(*S.work);
+        const uint32_t b = lds32(S.work);
         if (b >= P.nBlocks) break;
 
         uint32_t n;
@@ -531,93 +573,74 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
             fence_proxy_async();               // earlier generic-proxy reads of the buffer are done
             for (uint32_t c = 0; c < nChunks; c++) {
                 const uint32_t bytes = min(kTmaChunk, bulk - c * kTmaChunk);
-                const uint32_t bar = smem_u32(&S.mbar[c]);
+                const uint32_t bar = S.mbar + c * 8u;
                 mbar_expect_tx(bar, bytes);
-                tma_load_1d(smem_u32(S.in32) + c * kTmaChunk, gsrc + c * kTmaChunk, bytes, bar);
+                tma_load_1d(S.in + c * kTmaChunk, gsrc + c * kTmaChunk, bytes, bar);
             }
         }
         if (tid >= 32 && tid < 32 + (n - bulk))
-            reinterpret_cast<uint8_t *>(S.in32)[bulk + tid - 32] = gsrc[bulk + tid - 32];
-        {
-            uint4 *t = reinterpret_cast<uint4 *>(S.tabL);    // tabL and tabS are contiguous
-            const uint4 ff = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            for (uint32_t i = tid; i < (kSmemTabL + kSmemTabS) / 16; i += kThreads) t[i] = ff;
-        }
-        if (tid < 4) S.task[tid] = 0u;
+            sts8(S.in + bulk + tid - 32, gsrc[bulk + tid - 32]);
+        for (uint32_t i = tid; i < (kSmemTabL + kSmemTabS) / 16; i += kThreads)    // tabL and tabS are contiguous
+            sts128(S.tabL + i * 16u, 0xFFFFFFFFu);
+        if (tid < 2) sts32(S.task + tid * 4u, 0u);
         __syncthreads();
 
         const uint32_t nh = n >= 8 ? n - 7 : 0;
         const uint32_t nW = (n + kWindow - 1) / kWindow;
         uint32_t chunksSeen = 0;
-        ParseCarry pc = {0, 0, 0, 0};
+        uint32_t cursor = 0;                   // P1: first position the parser has not consumed yet
+        EmitCarry ec = {0, 0, 0};              // P2
 
         unsigned long long busy = 0, blockStart = clock64();
-        for (uint32_t t = 0; t < nW + 3; t++) {
+        for (uint32_t t = 0; t < nW + 4; t++) {
             const unsigned long long c0 = clock64();
             if (warp < kEhWarps) {
                 // bytes this stage may touch: hashing window t reads < (t+1)*1024 + 11, extending
                 // window t-2 reads < (t-1)*1024 + extCap + 36 + 3
                 const uint32_t need = min(bulk, (t + 1) * kWindow + 16u);
                 const uint32_t wantChunks = (need + kTmaChunk - 1) / kTmaChunk;
-                while (chunksSeen < wantChunks) { mbar_wait(smem_u32(&S.mbar[chunksSeen]), (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
-                // One task queue per stage, heaviest first: extension groups of window t-2, their
-                // jump-link groups, then the hash groups of window t.  Jump task g only needs extension
-                // tasks g-8..g (a match is at most 256 bytes long), tracked in a completion bitmask, so
-                // it almost never waits; groups of the previous window were finished a stage ago.
-                const bool haveE = t >= 2 && t - 2 < nW;
-                const uint32_t nE = haveE ? kGroups : 0u;
-                const uint32_t nH = t < nW ? kGroups : 0u;
-                const uint32_t nAll = 2u * nE + nH;
-                const uint32_t ctr = smem_u32(&S.task[(t & 1u) * 2u]);
-                volatile unsigned int *done = &S.task[(t & 1u) * 2u + 1u];
+                while (chunksSeen < wantChunks) { mbar_wait(S.mbar + chunksSeen * 8u, (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
+                // One task queue per stage, heaviest first: the extension groups of window t-2, then the
+                // hash groups of window t.
+                const uint32_t nE = (t >= 2 && t - 2 < nW) ? kGroups : 0u;
+                const uint32_t nAll = nE + (t < nW ? kGroups : 0u);
+                const uint32_t ctr = S.task + (t & 1u) * 4u;
                 for (;;) {
                     const uint32_t id = pop_task(ctr, lane);
                     if (id >= nAll) break;
-#ifdef B200SP_ORDER_EHJ
-                    // order E, H, J
-                    const uint32_t jLo = nE + nH, hLo = nE;
-#else
-                    const uint32_t jLo = nE, hLo = 2u * nE;
-#endif
                     if (id < nE) {
                         const uint32_t wdx = t - 2;
-                        stage_extend(S, wdx & (kRing - 1), id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap);
-                        __syncwarp();
-                        if (lane == 0) { __threadfence_block(); atomicOr(const_cast<unsigned int *>(done), 1u << id); }
-                    } else if (id >= jLo && id < jLo + nE) {
-                        const uint32_t g = id - jLo;
-                        const uint32_t need = (g >= 8u ? 0x1FFu << (g - 8u) : (2u << g) - 1u);
-                        while ((*done & need) != need) __nanosleep(B200SP_SPIN_NS);
-                        __threadfence_block();
-                        stage_jump(S, t - 2, g, lane, P.minMatch, P.lazyDepth);
+                        stage_extend(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap);
                     } else {
-                        const uint32_t g = id - hLo;
-                        stage_hash(S, t & (kRing - 1), g, lane, t * kWindow + g * 32u + lane, nh, P.shortMask);
+                        const uint32_t g = id - nE;
+                        stage_hash(S, t, g, lane, t * kWindow + g * 32u + lane, nh, P.shortMask);
                     }
                 }
             } else if (warp == kWarpTabL) {
-                if (t >= 1 && t - 1 < nW) stage_table(S.ring0, S.tabL, (t - 1) & (kRing - 1), lane, (t - 1) * kWindow);
+                if (t >= 1 && t - 1 < nW) stage_table(S, S.tabL, 0u, t - 1, lane);
             } else if (warp == kWarpTabS) {
-                if (t >= 1 && t - 1 < nW) stage_table(S.ring1, S.tabS, (t - 1) & (kRing - 1), lane, (t - 1) * kWindow);
+                if (t >= 1 && t - 1 < nW) stage_table(S, S.tabS, 1u, t - 1, lane);
+            } else if (warp == kWarpEntries) {
+                if (lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, 0u);   // next stage's queue (nobody touches it now)
+                if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, lane, cursor, P.minMatch, P.lazyDepth);
             } else {
-                if (lane < 2) S.task[((t + 1u) & 1u) * 2u + lane] = 0u;   // next stage's queues (nobody touches them now)
-                if (t >= 3) stage_parse(S, (t - 3) & (kRing - 1), lane, (t - 3) * kWindow, pc, out);
+                if (t >= 4) stage_emit(S, t - 4, lane, ec, out);
             }
             busy += clock64() - c0;
             __syncthreads();
         }
 
         if (P.roleCycles && lane == 0) {
-            const int role = warp < kEhWarps ? 0 : (warp - kEhWarps + 1);
+            const int role = warp < kEhWarps ? 0 : (warp - kEhWarps + 1);     // 0 EH, 1 TL, 2 TS, 3 P1, 4 P2
             atomicAdd(&P.roleCycles[role], busy);
-            if (warp == kWarpParse) { atomicAdd(&P.roleCycles[4], clock64() - blockStart); atomicAdd(&P.roleCycles[5], (unsigned long long)(nW + 3)); }
+            if (warp == kWarpEmit) { atomicAdd(&P.roleCycles[5], clock64() - blockStart); atomicAdd(&P.roleCycles[6], (unsigned long long)(nW + 4)); }
         }
-        if (warp == kWarpParse && lane == 0) {
-            out[pc.nOut] = make_uint4(0u, n - pc.anchor, 0u, 0u);   // trailing literals / block delimiter
-            P.counts[b] = pc.nOut + 1u;
+        if (warp == kWarpEmit && lane == 0) {
+            out[ec.nOut] = make_uint4(0u, n - ec.anchor, 0u, 0u);   // trailing literals / block delimiter
+            P.counts[b] = ec.nOut + 1u;
         }
         // every issued chunk must have landed before its mbarrier is re-armed for the next block
-        if (warp == 0) while (chunksSeen < nChunks) { mbar_wait(smem_u32(&S.mbar[chunksSeen]), (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
+        if (warp == 0) while (chunksSeen < nChunks) { mbar_wait(S.mbar + chunksSeen * 8u, (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
         tmaParity ^= (1u << nChunks) - 1u;   // only the barriers armed for this block changed phase
     }
 }

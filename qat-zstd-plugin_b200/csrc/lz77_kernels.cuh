@@ -15,7 +15,7 @@ namespace b200sp {
 constexpr uint32_t kBlockMax      = 1u << 17;   // ZSTD_BLOCKSIZE_MAX
 constexpr uint32_t kWindow        = 1024;       // positions per pipeline window
 constexpr uint32_t kGroups        = kWindow / 32;
-constexpr uint32_t kRing          = 4;          // windows in flight: hash, table, extend, parse
+constexpr uint32_t kRingC         = 4;          // candidate/match ring: windows in flight between hash and entries
 constexpr uint32_t kLongBits      = 14;
 constexpr uint32_t kShortBits     = 14;
 constexpr uint32_t kProbe         = 16;         // bytes compared per candidate before a winner is picked
@@ -25,23 +25,26 @@ constexpr uint32_t kTmaChunk      = 16384;
 constexpr uint32_t kTmaChunks     = kBlockMax / kTmaChunk;
 
 #ifndef B200SP_EH_WARPS
-#define B200SP_EH_WARPS 29
+#define B200SP_EH_WARPS 28
 #endif
-constexpr int kEhWarps   = B200SP_EH_WARPS;                  // hash + extension warps
-constexpr int kWarpTabL  = kEhWarps;            // serial owner of the long-hash table
-constexpr int kWarpTabS  = kEhWarps + 1;        // serial owner of the short-hash table
-constexpr int kWarpParse = kEhWarps + 2;        // speculative lane-parallel parser + emitter
-constexpr int kNumWarps  = kEhWarps + 3;
-constexpr int kThreads   = kNumWarps * 32;
+constexpr int kEhWarps     = B200SP_EH_WARPS;   // hash + extension warps
+constexpr int kWarpTabL    = kEhWarps;          // serial owner of the long-hash table
+constexpr int kWarpTabS    = kEhWarps + 1;      // serial owner of the short-hash table
+constexpr int kWarpEntries = kEhWarps + 2;      // P1: lazy decisions + group entries (speculative, lane-parallel)
+constexpr int kWarpEmit    = kEhWarps + 3;      // P2: scans + ZSTD_Sequence stores
+constexpr int kNumWarps    = kEhWarps + 4;
+constexpr int kThreads     = kNumWarps * 32;
 
 // Shared-memory carve-up (bytes)
 constexpr uint32_t kSmemInput   = kBlockMax + kInputPad;
 constexpr uint32_t kSmemTabL    = (1u << kLongBits) * 2;
 constexpr uint32_t kSmemTabS    = (1u << kShortBits) * 2;
-constexpr uint32_t kSmemRing    = kRing * 2 * kWindow * 4;
-constexpr uint32_t kSmemGmax    = kRing * kGroups * 4;
+constexpr uint32_t kSmemRingH   = 2 * kWindow * 4;        // hash words, H -> T
+constexpr uint32_t kSmemRingC   = kRingC * kWindow * 4;   // candidates -> packed prefix maxima, H/T -> E -> P1
+constexpr uint32_t kSmemRingL   = 2 * kWindow * 4;        // memoised parse decisions, P1 -> P2
+constexpr uint32_t kSmemGroup   = (2 * kRingC + 4) * kGroups * 4;   // gmax, gown, hasA, entA
 constexpr uint32_t kSmemMisc    = 128;          // mbarriers + work-item slot + task counters
-constexpr uint32_t kSmemTotal   = kSmemInput + kSmemTabL + kSmemTabS + kSmemRing + kSmemGmax + kSmemMisc;
+constexpr uint32_t kSmemTotal   = kSmemInput + kSmemTabL + kSmemTabS + kSmemRingH + kSmemRingC + kSmemRingL + kSmemGroup + kSmemMisc;
 static_assert(kSmemTotal <= 232448, "exceeds 227 KB of shared memory per CTA");
 
 struct ParseParams {

@@ -332,13 +332,14 @@ int b200sp_verify_device(b200sp_engine *e, const void *d_src, uint64_t totalSize
     return B200SP_OK;
 }
 
-/* developer profiling (not in the public header): copies the 6 role counters and zeroes them */
+/* developer profiling (not in the public header): copies the 8 role counters (busy cycles of EH, TL, TS, P1,
+ * P2; block wall cycles; stage count; spare) and zeroes them */
 int b200sp_debug_role_cycles(b200sp_engine *e, unsigned long long *out6)
 {
     if (!e || !out6) return B200SP_EINVAL;
     cudaStreamSynchronize(e->stream);
-    cudaMemcpy(out6, reinterpret_cast<unsigned long long *>(e->d_work) + 1, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    cudaMemset(reinterpret_cast<unsigned long long *>(e->d_work) + 1, 0, 6 * sizeof(unsigned long long));
+    cudaMemcpy(out6, reinterpret_cast<unsigned long long *>(e->d_work) + 1, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemset(reinterpret_cast<unsigned long long *>(e->d_work) + 1, 0, 8 * sizeof(unsigned long long));
     return B200SP_OK;
 }
 
