@@ -15,7 +15,8 @@
  *       carry  c_j   = farthest-reaching match of the previous 8 groups, re-based to group j;
  *       B(p)         = max(prefix maximum at p, c_j);   has_j = gown_j | {lanes covered by c_j};
  *       walk(e)      = greedy/lazy parse of group j entered at e; every decision is memoised as a link
- *                      word {end : 9 | take position : 5 | offset : 17} so a position is evaluated once;
+ *                      word (take {end : 9 | take position : 5 | offset : 17} or lazy hop {1 << 31 | next : 9})
+ *                      so a position is evaluated once;
  *       entries      = every lane guesses "entered at my first position"; guesses are corrected by a
  *                      prefix maximum over the exits of live lanes until nothing changes (= the serial
  *                      parse, because a walk depends only on where it is entered).
@@ -43,25 +44,22 @@ typedef struct {
     uint32_t minMatch, lazyDepth;
 } Group;
 
-/* one decision: cursor at local position p0 (a has-position) -> link word */
-static uint32_t eval_take(const Group *g, uint32_t p0)
+/* one decision: the cursor stands on local position p (a usable match starts there).  Either a take link
+ * {end:9 | take lane:5 | offset:17} or, when the lazy rule prefers a later start, a hop link
+ * {1 << 31 | next position << 22}; the look-ahead never leaves the group. */
+static uint32_t eval_step(const Group *g, uint32_t p)
 {
-    uint32_t p = p0;
-    for (;;) {
-        const uint32_t b0 = umax(g->pk[p], g->c);
-        if (g->lazyDepth >= 1) {
-            const int32_t g0 = gain_packed(b0, p);
-            uint32_t q = p + 1;
-            if (q < KGRP && ((g->has >> q) & 1u)) {
-                if (gain_packed(umax(g->pk[q], g->c), q) > g0 + 4) { p = q; continue; }
-                q = p + 2;
-                if (g->lazyDepth >= 2 && q < KGRP && ((g->has >> q) & 1u)) {
-                    if (gain_packed(umax(g->pk[q], g->c), q) > g0 + 7) { p = q; continue; }
-                }
-            }
+    const uint32_t b0 = umax(g->pk[p], g->c);
+    if (g->lazyDepth >= 1) {
+        const int32_t g0 = gain_packed(b0, p);
+        const uint32_t q1 = p + 1, q2 = p + 2;
+        if (q1 < KGRP && ((g->has >> q1) & 1u)) {
+            if (gain_packed(umax(g->pk[q1], g->c), q1) > g0 + 4) return 0x80000000u | (q1 << 22);
+            if (g->lazyDepth >= 2 && q2 < KGRP && ((g->has >> q2) & 1u) &&
+                gain_packed(umax(g->pk[q2], g->c), q2) > g0 + 7) return 0x80000000u | (q2 << 22);
         }
-        return ((b0 >> 23) << 22) | (p << 17) | (b0 & 0x1FFFFu);
     }
+    return ((b0 >> 23) << 22) | (p << 17) | (b0 & 0x1FFFFu);
 }
 
 /* walk of one group from local cursor `cur` (< 32); returns the local exit (>= 32) */
@@ -71,8 +69,8 @@ static uint32_t walk_exit(Group *g, uint32_t cur)
         const uint32_t m = g->has & (0xFFFFFFFFu << cur);
         if (!m) return KGRP;
         const uint32_t p0 = (uint32_t)__builtin_ctz(m);
-        if (!((g->visited >> p0) & 1u)) { g->link[p0] = eval_take(g, p0); g->visited |= 1u << p0; }
-        cur = g->link[p0] >> 22;
+        if (!((g->visited >> p0) & 1u)) { g->link[p0] = eval_step(g, p0); g->visited |= 1u << p0; }
+        cur = (g->link[p0] >> 22) & 0x1FFu;
     }
     return cur;
 }
@@ -172,6 +170,7 @@ size_t lanemodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t 
                     const uint32_t m = hasA[G] & (0xFFFFFFFFu << cur);
                     if (!m) break;
                     const uint32_t L = link[G * KGRP + (uint32_t)__builtin_ctz(m)];
+                    if (L >> 31) { cur = (L >> 22) & 0x1FFu; continue; }      /* hop: a later start is better */
                     const uint32_t p = segStart + ((L >> 17) & 31u), end = segStart + (L >> 22), off = L & 0x1FFFFu;
                     if (cnt[j] && p == lastEnd[j] && off == lastOff[j]) merges[j]++;
                     if (!cnt[j]) { firstPos[j] = p; firstOff[j] = off; }
@@ -194,6 +193,7 @@ size_t lanemodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t 
                     const uint32_t m = hasA[G] & (0xFFFFFFFFu << cur);
                     if (!m) break;
                     const uint32_t L = link[G * KGRP + (uint32_t)__builtin_ctz(m)];
+                    if (L >> 31) { cur = (L >> 22) & 0x1FFu; continue; }      /* hop: a later start is better */
                     const uint32_t p = segStart + ((L >> 17) & 31u), end = segStart + (L >> 22), off = L & 0x1FFFFu;
                     if (p == anchor && off == prevOff && anchor > 0) {
                         out[idx - 1].matchLength += end - p;     /* continuation (of this lane's or an earlier lane's sequence) */

@@ -37,6 +37,8 @@ def _load():
     l.seqmodel_params_for_level.argtypes = [c_int, POINTER(ModelParams)]
     l.seqmodel_block.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, POINTER(ModelParams)]
     l.seqmodel_block.restype = c_size_t
+    l.lanemodel_block.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, POINTER(ModelParams)]
+    l.lanemodel_block.restype = c_size_t
     l.oracle_sw_create.restype = c_void_p
     l.oracle_sw_free.argtypes = [c_void_p]
     l.oracle_sw_producer.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_size_t]
@@ -83,6 +85,18 @@ def model_block(data, level: int = 3) -> np.ndarray:
     n = lib.seqmodel_block(a.ctypes.data, a.size, out.ctypes.data, cap, ctypes.byref(prm))
     if n == ERROR:
         raise RuntimeError("seqmodel_block failed")
+    return out[:n].copy()
+
+
+def lane_model_block(data, level: int = 3) -> np.ndarray:
+    """Lane-level statement of the kernel's parse stage (oracle/lanemodel.c) on ONE block; must equal model_block."""
+    a = _u8(data)
+    cap = a.size // 3 + 8
+    out = np.zeros((cap, 4), np.uint32)
+    prm = model_params(level)
+    n = lib.lanemodel_block(a.ctypes.data, a.size, out.ctypes.data, cap, ctypes.byref(prm))
+    if n == ERROR:
+        raise RuntimeError("lanemodel_block failed")
     return out[:n].copy()
 
 

@@ -329,28 +329,24 @@ __device__ __forceinline__ int32_t gain_packed(uint32_t b, uint32_t lane)
     return static_cast<int32_t>(((b >> 23) - lane) * 4u) - static_cast<int32_t>(31 - __clz((b & 0x1FFFFu) + 1u));
 }
 
-// One decision: the cursor stands on local position p0 (a usable match starts there).  Applies the lazy
-// rule (look-ahead never leaves the group) and returns the link word {end:9 | take lane:5 | offset:17}.
-__device__ __forceinline__ uint32_t eval_take(uint32_t pkRow, uint32_t group, uint32_t p0, uint32_t c,
+// One decision: the cursor stands on local position p (a usable match starts there).  The lazy rule
+// (look-ahead never leaves the group) yields either a take link {end:9 | take lane:5 | offset:17} or a hop
+// link {1 << 31 | next position << 22}; the three packed words are loaded together.
+__device__ __forceinline__ uint32_t eval_step(uint32_t pkRow, uint32_t group, uint32_t p, uint32_t c,
                                               uint32_t has, uint32_t lazyDepth)
 {
-    uint32_t p = p0;
-    for (;;) {
-        const uint32_t b0 = max(lds32(pkRow + ring_byte(group, p)), c);
-        if (lazyDepth >= 1u) {
-            const int32_t g0 = gain_packed(b0, p);
-            const uint32_t q1 = p + 1u, q2 = p + 2u;
-            if (q1 < 32u && ((has >> q1) & 1u)) {
-                const uint32_t b1 = max(lds32(pkRow + ring_byte(group, q1)), c);
-                if (gain_packed(b1, q1) > g0 + 4) { p = q1; continue; }
-                if (lazyDepth >= 2u && q2 < 32u && ((has >> q2) & 1u)) {
-                    const uint32_t b2 = max(lds32(pkRow + ring_byte(group, q2)), c);
-                    if (gain_packed(b2, q2) > g0 + 7) { p = q2; continue; }
-                }
-            }
-        }
-        return ((b0 >> 23) << 22) | (p << 17) | (b0 & 0x1FFFFu);
-    }
+    const uint32_t q1 = p + 1u, q2 = p + 2u;
+    const uint32_t w0 = lds32(pkRow + ring_byte(group, p));
+    const uint32_t w1 = lds32(pkRow + ring_byte(group, min(q1, 31u)));
+    const uint32_t w2 = lds32(pkRow + ring_byte(group, min(q2, 31u)));
+    const uint32_t b0 = max(w0, c), b1 = max(w1, c), b2 = max(w2, c);
+    const int32_t g0 = gain_packed(b0, p), g1 = gain_packed(b1, q1), g2 = gain_packed(b2, q2);
+    const bool ok1 = lazyDepth >= 1u && q1 < 32u && ((has >> (q1 & 31u)) & 1u);
+    const bool ok2 = ok1 && lazyDepth >= 2u && q2 < 32u && ((has >> (q2 & 31u)) & 1u);
+    uint32_t L = ((b0 >> 23) << 22) | (p << 17) | (b0 & 0x1FFFFu);
+    if (ok1 && g1 > g0 + 4) L = 0x80000000u | (q1 << 22);
+    else if (ok2 && g2 > g0 + 7) L = 0x80000000u | (q2 << 22);
+    return L;
 }
 
 __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint32_t lane, uint32_t &cursor,
@@ -399,11 +395,11 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
                 uint32_t L;
                 if ((visited >> p0) & 1u) L = lds32(linkRow + ring_byte(lane, p0));
                 else {
-                    L = eval_take(pkRow, lane, p0, c, has, lazyDepth);
+                    L = eval_step(pkRow, lane, p0, c, has, lazyDepth);
                     sts32(linkRow + ring_byte(lane, p0), L);
                     visited |= 1u << p0;
                 }
-                cur = L >> 22;
+                cur = (L >> 22) & 0x1FFu;
             }
             exitPos = live ? segStart + cur : 0u;                    // passed-over lanes contribute nothing
         }
@@ -451,6 +447,7 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
             const uint32_t m = has & (0xFFFFFFFFu << cur);
             if (!m) break;
             const uint32_t L = lds32(linkRow + ring_byte(lane, __ffs(m) - 1));
+            if (L >> 31) { cur = (L >> 22) & 0x1FFu; continue; }         // hop: a later start is better (lazy)
             const uint32_t p = segStart + ((L >> 17) & 31u), end = segStart + (L >> 22), off = L & 0x1FFFFu;
             if (cnt && p == lastEnd && off == lastOff) merges++;
             if (!cnt) { firstPos = p; firstOff = off; }
@@ -495,6 +492,7 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
             const uint32_t m = has & (0xFFFFFFFFu << cur);
             if (!m) break;
             const uint32_t L = lds32(linkRow + ring_byte(lane, __ffs(m) - 1));
+            if (L >> 31) { cur = (L >> 22) & 0x1FFu; continue; }         // hop
             const uint32_t p = segStart + ((L >> 17) & 31u), end = segStart + (L >> 22), o = L & 0x1FFFFu;
             const uint32_t lit = p - anchor, len = end - p;
             if (lit == 0 && o == prevOff && anchor > 0) {
@@ -541,6 +539,9 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         S.task = p;
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // Role of this warp: 0 = hash/extend pool, 1 = long table, 2 = short table, 3 = entries (P1), 4 = emit (P2).
+    // (Which scheduler the four serial warps sit on made no measurable difference.)
+    const uint32_t role = warp < kEhWarps ? 0u : warp - kEhWarps + 1u;
 
     if (tid == 0) {
         for (uint32_t c = 0; c < kTmaChunks; c++) mbar_init(S.mbar + c * 8u, 1);
@@ -594,7 +595,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         unsigned long long busy = 0, blockStart = clock64();
         for (uint32_t t = 0; t < nW + 4; t++) {
             const unsigned long long c0 = clock64();
-            if (warp < kEhWarps) {
+            if (role == 0u) {
                 // bytes this stage may touch: hashing window t reads < (t+1)*1024 + 11, extending
                 // window t-2 reads < (t-1)*1024 + extCap + 36 + 3
                 const uint32_t need = min(bulk, (t + 1) * kWindow + 16u);
@@ -616,11 +617,11 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                         stage_hash(S, t, g, lane, t * kWindow + g * 32u + lane, nh, P.shortMask);
                     }
                 }
-            } else if (warp == kWarpTabL) {
+            } else if (role == 1u) {
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabL, 0u, t - 1, lane);
-            } else if (warp == kWarpTabS) {
+            } else if (role == 2u) {
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabS, 1u, t - 1, lane);
-            } else if (warp == kWarpEntries) {
+            } else if (role == 3u) {
                 if (lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, 0u);   // next stage's queue (nobody touches it now)
                 if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, lane, cursor, P.minMatch, P.lazyDepth);
             } else {
@@ -631,11 +632,10 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         }
 
         if (P.roleCycles && lane == 0) {
-            const int role = warp < kEhWarps ? 0 : (warp - kEhWarps + 1);     // 0 EH, 1 TL, 2 TS, 3 P1, 4 P2
             atomicAdd(&P.roleCycles[role], busy);
-            if (warp == kWarpEmit) { atomicAdd(&P.roleCycles[5], clock64() - blockStart); atomicAdd(&P.roleCycles[6], (unsigned long long)(nW + 4)); }
+            if (role == 4u) { atomicAdd(&P.roleCycles[5], clock64() - blockStart); atomicAdd(&P.roleCycles[6], (unsigned long long)(nW + 4)); }
         }
-        if (warp == kWarpEmit && lane == 0) {
+        if (role == 4u && lane == 0) {
             out[ec.nOut] = make_uint4(0u, n - ec.anchor, 0u, 0u);   // trailing literals / block delimiter
             P.counts[b] = ec.nOut + 1u;
         }

@@ -142,3 +142,26 @@ def test_golden_vectors(oracle):
         lz = open(os.path.join(GOLDEN, name + ".lz4s"), "rb").read()
         dec = oracle.declz4s(lz)
         assert dec is not None and (dec[:, :3] == want[:, :3]).all(), name
+
+
+# ---- the lane-level statement of the kernel's parse stage (oracle/lanemodel.c) against the serial model ----
+LANE_KINDS = KINDS + [(lambda n, s: datagen.zeros(n), 0), (lambda n, s: datagen.periodic(n, 100), 0),
+                      (datagen.mixed_corpus, 5)]
+
+
+@pytest.mark.parametrize("level", [1, 3, 6, 12])
+@pytest.mark.parametrize("maker,seed", LANE_KINDS)
+def test_lane_model_equals_serial_model(oracle, maker, seed, level):
+    data = maker(BLOCK, seed)
+    want = oracle.model_block(data, level)
+    got = oracle.lane_model_block(data, level)
+    assert got.shape == want.shape and (got == want).all()
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 31, 32, 33, 1023, 1024, 1025, 4097, 70001, 131071])
+def test_lane_model_ragged_sizes(oracle, n):
+    for maker, seed in ((datagen.text_like, 11), (datagen.records, 12)):
+        data = maker(max(n, 1), seed)[:n]
+        want = oracle.model_block(data, 3)
+        got = oracle.lane_model_block(data, 3)
+        assert got.shape == want.shape and (got == want).all()
