@@ -96,6 +96,18 @@ void QZSTD_hintSource(void *sequenceProducerState, const void *src, size_t srcSi
 void QZSTD_getStats(const void *sequenceProducerState, unsigned long long *calls,
                     unsigned long long *errors, unsigned long long *batched);
 
+/* Whole-buffer counterpart of stock ZSTD_generateSequences(): parses ALL blocks of [src, src + srcSize)
+ * (blockSize bytes each, 0 = 128 KiB, blocks independent of each other) in one GPU batch and writes one
+ * ZSTD_Sequence array in which every block ends with its {0, trailing literals, 0} entry, i.e. the
+ * explicit-block-delimiter format ZSTD_compressSequences() accepts with ZSTD_c_blockDelimiters =
+ * ZSTD_sf_explicitBlockDelimiters.  This is step 4 of the reference's flow chart ("Compress Sequences
+ * API", docs/images/qatzstdplugin.png) without one synchronous callback per block.
+ * outSeqsCapacity >= ZSTD_sequenceBound(srcSize) + number of blocks always suffices.  Returns the number
+ * of entries, or ZSTD_SEQUENCE_PRODUCER_ERROR under the same conditions as qatSequenceProducer
+ * (level outside 1..12, no device, capacity too small, device error). */
+size_t QZSTD_generateSequences(void *sequenceProducerState, ZSTD_Sequence *outSeqs, size_t outSeqsCapacity,
+                               const void *src, size_t srcSize, size_t blockSize, int compressionLevel);
+
 #endif /* QATSEQPROD_H */
 
 #if defined (__cplusplus)

@@ -48,6 +48,8 @@ def _load():
     l.oracle_compress_with_producer.argtypes = [c_void_p, c_size_t, c_size_t, c_int, c_void_p, c_void_p, c_int, c_int,
                                                 c_int, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_int)]
     l.oracle_compress_with_producer.restype = c_size_t
+    l.oracle_compress_sequences.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, POINTER(c_int)]
+    l.oracle_compress_sequences.restype = c_size_t
     l.oracle_validate_sequences.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, POINTER(c_size_t)]
     l.oracle_validate_sequences.restype = c_int
     l.oracle_declz4s.argtypes = [c_void_p, c_size_t, c_void_p, ctypes.c_uint]
@@ -138,6 +140,15 @@ def compress_with_producer(data, producer_ptr, state, *, chunk: int = 1 << 17, l
     n = lib.oracle_compress_with_producer(a.ctypes.data, a.size, chunk, level, producer_ptr, state, repcodes, fallback,
                                           validate_sequences, ctypes.byref(calls), ctypes.byref(errs), ctypes.byref(ok))
     return {"csize": None if n == ERROR else n, "calls": calls.value, "errors": errs.value, "round_trip": bool(ok.value)}
+
+
+def compress_sequences(data, seqs: np.ndarray, level: int = 3, repcodes: int = 1):
+    """ZSTD_compressSequences over an explicit-delimiter array + round trip -> {"csize", "round_trip"}."""
+    a = _u8(data)
+    s = np.ascontiguousarray(seqs, dtype=np.uint32)
+    ok = c_int(0)
+    c = lib.oracle_compress_sequences(a.ctypes.data, a.size, s.ctypes.data, s.shape[0], level, repcodes, ctypes.byref(ok))
+    return {"csize": None if c == ERROR else int(c), "round_trip": bool(ok.value)}
 
 
 def sw_producer_ptr():

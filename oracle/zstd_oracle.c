@@ -291,3 +291,33 @@ size_t oracle_enclz4s(unsigned char *dst, size_t cap, const ZSTD_Sequence *seqs,
     }
     return pos;
 }
+
+/* Whole-buffer hand-off check: ZSTD_compressSequences over one ZSTD_Sequence array with explicit block
+ * delimiters (what QZSTD_generateSequences produces), then ZSTD_decompress + memcmp.  Returns the
+ * compressed size, or (size_t)-1 when libzstd rejects the sequences. */
+size_t oracle_compress_sequences(const void *src, size_t srcSize, const ZSTD_Sequence *seqs, size_t nbSeqs,
+                                 int level, int repcodeMode, int *roundTripOk)
+{
+    if (roundTripOk) *roundTripOk = 0;
+    ZSTD_CCtx *zc = ZSTD_createCCtx();
+    size_t dstCap = ZSTD_compressBound(srcSize) + 64 * (srcSize / (1u << 17) + 1);
+    unsigned char *dst = (unsigned char *)malloc(dstCap);
+    unsigned char *back = (unsigned char *)malloc(srcSize ? srcSize : 1);
+    size_t c = (size_t)-1;
+    if (!zc || !dst || !back) goto out;
+    if (ZSTD_isError(ZSTD_CCtx_setParameter(zc, ZSTD_c_compressionLevel, level))) goto out;
+    if (ZSTD_isError(ZSTD_CCtx_setParameter(zc, ZSTD_c_blockDelimiters, 1))) goto out;          /* explicit */
+    if (ZSTD_isError(ZSTD_CCtx_setParameter(zc, ZSTD_c_validateSequences, 1))) goto out;
+    if (ZSTD_isError(ZSTD_CCtx_setParameter(zc, ZSTD_c_searchForExternalRepcodes, repcodeMode))) goto out;
+    c = ZSTD_compressSequences(zc, dst, dstCap, seqs, nbSeqs, src, srcSize);
+    if (ZSTD_isError(c)) { c = (size_t)-1; goto out; }
+    if (roundTripOk) {
+        size_t d = ZSTD_decompress(back, srcSize, dst, c);
+        *roundTripOk = (!ZSTD_isError(d) && d == srcSize && memcmp(back, src, srcSize) == 0);
+    }
+out:
+    ZSTD_freeCCtx(zc);
+    free(dst);
+    free(back);
+    return c;
+}

@@ -82,6 +82,11 @@ size_t oracle_declz4s(ZSTD_Sequence *outSeqs, size_t outSeqsCapacity,
 size_t oracle_enclz4s(unsigned char *dst, size_t dstCapacity,
                       const ZSTD_Sequence *seqs, size_t nbSeqs);
 
+/* ZSTD_compressSequences over an explicit-delimiter sequence array (the hand-off format of
+ * QZSTD_generateSequences) + decompress + compare.  Returns the compressed size or (size_t)-1. */
+size_t oracle_compress_sequences(const void *src, size_t srcSize, const ZSTD_Sequence *seqs, size_t nbSeqs,
+                                 int level, int repcodeMode, int *roundTripOk);
+
 #if defined(__cplusplus)
 }
 #endif

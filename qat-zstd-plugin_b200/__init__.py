@@ -79,6 +79,8 @@ def _load():
     l.QZSTD_hintSource.restype = None
     l.QZSTD_getStats.argtypes = [c_void_p, POINTER(c_ulonglong), POINTER(c_ulonglong), POINTER(c_ulonglong)]
     l.QZSTD_getStats.restype = None
+    l.QZSTD_generateSequences.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int]
+    l.QZSTD_generateSequences.restype = c_size_t
     # --- b200seqprod.h
     l.b200sp_driver_device_count.restype = c_int
     l.b200sp_device_count.restype = c_int
@@ -110,7 +112,7 @@ lib = _load()
 # Every symbol include/qatseqprod.h and include/b200seqprod.h declare (checked by the CPU tests).
 EXPORTED_SYMBOLS = [
     "QZSTD_version", "QZSTD_startQatDevice", "QZSTD_stopQatDevice", "QZSTD_createSeqProdState",
-    "QZSTD_freeSeqProdState", "qatSequenceProducer", "QZSTD_hintSource", "QZSTD_getStats",
+    "QZSTD_freeSeqProdState", "qatSequenceProducer", "QZSTD_hintSource", "QZSTD_getStats", "QZSTD_generateSequences",
     "b200sp_driver_device_count", "b200sp_device_count", "b200sp_engine_create", "b200sp_engine_destroy",
     "b200sp_engine_device", "b200sp_engine_sm_count", "b200sp_parse_device", "b200sp_sync",
     "b200sp_parse_host", "b200sp_expand", "b200sp_verify_device", "b200sp_error_string", "b200sp_version",
@@ -225,6 +227,20 @@ class QatSeqProd:
         a, b, c = c_ulonglong(), c_ulonglong(), c_ulonglong()
         lib.QZSTD_getStats(state, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
         return {"calls": a.value, "errors": b.value, "batched": c.value}
+
+    @staticmethod
+    def generateSequences(state: int, data, level: int = 3, block_size: int = 0):
+        """Whole-buffer hand-off (QZSTD_generateSequences): sequences[n, 4] u32 with explicit block
+        delimiters, or None on ZSTD_SEQUENCE_PRODUCER_ERROR."""
+        import numpy as np
+        a = np.frombuffer(data, dtype=np.uint8)
+        bs = block_size or (1 << 17)
+        cap = a.size // 3 + 8 * ((a.size + bs - 1) // bs) + 16
+        out = np.zeros((cap, 4), np.uint32)
+        n = lib.QZSTD_generateSequences(state, out.ctypes.data, cap, a.ctypes.data, a.size, block_size, level)
+        if n == ctypes.c_size_t(-1).value:
+            return None
+        return out[:n]
 
     @staticmethod
     def qatSequenceProducer(state, out_seqs, capacity, src, src_size, dict_=None, dict_size=0, level=3,

@@ -141,6 +141,32 @@ static size_t producer_error(QZSTD_State_T *s)
     return ZSTD_SEQUENCE_PRODUCER_ERROR;
 }
 
+/* device status: fail fast, retry the start every 1000th refused block (:1140-1152); then make sure the
+ * state owns an engine.  Returns 0 when the block can be offloaded. */
+static int device_ready(QZSTD_State_T *s)
+{
+    if (g_process.status != QZSTD_OK) {
+        s->failOffloadCnt++;
+        if (s->failOffloadCnt >= NUM_BLOCK_OF_RETRY_INTERVAL) {
+            s->failOffloadCnt = 0;
+            if (QZSTD_startQatDevice() != QZSTD_OK) {
+                QZSTD_LOG(1, "Tried to restart the device, but failed\n");
+                return -1;
+            }
+        } else {
+            QZSTD_LOG(1, "The device was not successfully started\n");
+            return -1;
+        }
+    }
+    if (!s->engine) {
+        if (b200sp_engine_create(0, &s->engine) != B200SP_OK) {
+            QZSTD_LOG(1, "Failed to create engine: %s\n", b200sp_error_string());
+            return -1;
+        }
+    }
+    return 0;
+}
+
 size_t qatSequenceProducer(
     void *sequenceProducerState, ZSTD_Sequence *outSeqs, size_t outSeqsCapacity,
     const void *src, size_t srcSize,
@@ -168,27 +194,7 @@ size_t qatSequenceProducer(
         return producer_error(s);
     }
 
-    /* device status: fail fast, retry the start every 1000th refused block (:1140-1152) */
-    if (g_process.status != QZSTD_OK) {
-        s->failOffloadCnt++;
-        if (s->failOffloadCnt >= NUM_BLOCK_OF_RETRY_INTERVAL) {
-            s->failOffloadCnt = 0;
-            if (QZSTD_startQatDevice() != QZSTD_OK) {
-                QZSTD_LOG(1, "Tried to restart the device, but failed\n");
-                return producer_error(s);
-            }
-        } else {
-            QZSTD_LOG(1, "The device was not successfully started\n");
-            return producer_error(s);
-        }
-    }
-
-    if (!s->engine) {
-        if (b200sp_engine_create(0, &s->engine) != B200SP_OK) {
-            QZSTD_LOG(1, "Failed to create engine: %s\n", b200sp_error_string());
-            return producer_error(s);
-        }
-    }
+    if (device_ready(s) != 0) return producer_error(s);
 
     /* look-ahead: serve the block from (or first build) the batch over the hinted buffer */
     {
@@ -237,4 +243,39 @@ size_t qatSequenceProducer(
     }
     QZSTD_LOG(2, "Produced %lu sequences\n", (unsigned long)rc);
     return rc;
+}
+
+size_t QZSTD_generateSequences(void *sequenceProducerState, ZSTD_Sequence *outSeqs, size_t outSeqsCapacity,
+                               const void *src, size_t srcSize, size_t blockSize, int compressionLevel)
+{
+    QZSTD_State_T *s = (QZSTD_State_T *)sequenceProducerState;
+    b200sp_result all;
+    size_t total, b;
+
+    if (s) s->calls++;
+    if (blockSize == 0) blockSize = ZSTD_BLOCKSIZE_MAX;
+    if (compressionLevel < COMP_LVL_MINIMUM || compressionLevel > COMP_LVL_MAXIMUM) {
+        QZSTD_LOG(1, "Only L1-L12 can be offloaded, current compression level: %d\n", compressionLevel);
+        return producer_error(s);
+    }
+    if (!s || !outSeqs || !src || srcSize == 0 || blockSize > ZSTD_BLOCKSIZE_MAX || force_error()) {
+        return producer_error(s);
+    }
+    if (device_ready(s) != 0) return producer_error(s);
+
+    if (b200sp_parse_host(s->engine, src, srcSize, (uint32_t)blockSize, compressionLevel, &all) != B200SP_OK) {
+        QZSTD_LOG(1, "Batch parse failed: %s\n", b200sp_error_string());
+        return producer_error(s);
+    }
+    s->batchLevel = 0;              /* the engine's result buffers were reused */
+    total = (size_t)all.offsets[all.nBlocks];
+    if (total > outSeqsCapacity) {
+        QZSTD_LOG(1, "Sequence count exceeds capacity\n");
+        return producer_error(s);
+    }
+    /* the blocks' entries are already consecutive in the wire array, each block ending with its
+     * {0, trailing literals, 0} entry: one expansion pass is the whole hand-off */
+    b200sp_expand(all.packed, total, (b200sp_sequence *)outSeqs);
+    for (b = 0; b < all.nBlocks; b++) s->batched++;
+    return total;
 }

@@ -134,3 +134,63 @@ def test_wire_format_expand(pkg):
     out = np.zeros((4, 4), np.uint32)
     pkg.lib.b200sp_expand(packed.ctypes.data, 4, out.ctypes.data)
     assert (out == seqs.astype(np.uint32)).all()
+
+
+def test_fuzz_adapter_exports_and_no_device_behaviour(pkg):
+    """The five FUZZ_* hooks of /root/reference/test/fuzzing/qatseqprodfuzzer.c:41-74 live in a separate
+    object (libqatseqprodfuzzer.{so,a}), not in libqatseqprod.so."""
+    d = os.path.dirname(pkg.LIB_PATH)
+    fz = ctypes.CDLL(os.path.join(d, "libqatseqprodfuzzer.so"))
+    assert os.path.exists(os.path.join(d, "libqatseqprodfuzzer.a"))
+    names = ["FUZZ_seqProdSetup", "FUZZ_seqProdTearDown", "FUZZ_createSeqProdState", "FUZZ_freeSeqProdState",
+             "FUZZ_thirdPartySeqProd"]
+    for n in names:
+        assert hasattr(fz, n)
+        assert not hasattr(pkg.lib, n), f"{n} must not be exported by libqatseqprod.so"
+    fz.FUZZ_seqProdSetup.restype = ctypes.c_size_t
+    fz.FUZZ_seqProdTearDown.restype = ctypes.c_size_t
+    fz.FUZZ_createSeqProdState.restype = ctypes.c_void_p
+    fz.FUZZ_freeSeqProdState.argtypes = [ctypes.c_void_p]
+    fz.FUZZ_freeSeqProdState.restype = ctypes.c_size_t
+    fz.FUZZ_thirdPartySeqProd.restype = ctypes.c_size_t
+    fz.FUZZ_thirdPartySeqProd.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                          ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_size_t]
+    if gpu_present():
+        return
+    assert fz.FUZZ_seqProdSetup() == ctypes.c_size_t(-1).value        # QZSTD_FAIL as size_t: the fuzzers assert == 0
+    st = fz.FUZZ_createSeqProdState()
+    assert st
+    src = np.zeros(4096, np.uint8)
+    out = np.zeros((2000, 4), np.uint32)
+    assert fz.FUZZ_thirdPartySeqProd(st, out.ctypes.data, 2000, src.ctypes.data, src.size, None, 0, 3, 1 << 17) == \
+        pkg.ZSTD_SEQUENCE_PRODUCER_ERROR
+    assert fz.FUZZ_freeSeqProdState(st) == 0
+    assert fz.FUZZ_seqProdTearDown() == 0
+
+
+@pytest.mark.skipif(gpu_present(), reason="no-device behaviour; covered by the gpu tests on a B200")
+def test_generate_sequences_without_device(pkg):
+    q = pkg.QatSeqProd
+    st = q.createSeqProdState()
+    assert q.generateSequences(st, b"abcdabcdabcd" * 1000, level=3) is None
+    assert q.generateSequences(st, b"abcdabcdabcd" * 1000, level=13) is None
+    assert q.getStats(st)["errors"] == 2
+    q.freeSeqProdState(st)
+
+
+def test_compress_sequences_hand_off_format(oracle):
+    """The hand-off format itself, on the CPU: per-block software sequences, each block ending with its
+    {0, literals, 0} entry, concatenated, go through ZSTD_compressSequences (explicit delimiters,
+    validation on) and decompress to the input."""
+    from tests import datagen
+    data = datagen.mixed_corpus(3 * (1 << 17) + 4321, seed=4)
+    blocks = [data[o:o + (1 << 17)] for o in range(0, len(data), 1 << 17)]
+    seqs = np.concatenate([oracle.sw_block(b, 3) for b in blocks])
+    r = oracle.compress_sequences(data, seqs, level=3)
+    assert r["round_trip"] and r["csize"] is not None
+    ref = oracle.chunked_compress(data, 1 << 17, 3)
+    assert 0.95 < r["csize"] / ref < 1.01      # one frame instead of one per chunk: a little smaller
+    bad = seqs.copy()
+    bad[5, 0] += 1                                # a wrong offset must not survive validation + round trip
+    r2 = oracle.compress_sequences(data, bad, level=3)
+    assert not r2["round_trip"]

@@ -153,3 +153,31 @@ def test_producer_argument_rejection_on_gpu(pkg):
     finally:
         q.freeSeqProdState(st)
         q.stopQatDevice()
+
+
+def test_generate_sequences_hand_off(pkg, oracle):
+    """QZSTD_generateSequences (the reference's flow-chart step 4 "Compress Sequences API"):
+    one GPU batch -> one explicit-delimiter array -> ZSTD_compressSequences, no per-block callback.  The array
+    is the concatenation of the per-block model outputs; the frame round-trips and is as small as the one the
+    registered producer gives."""
+    data = datagen.mixed_corpus(9 * BLOCK + 1234, seed=41)
+    q = pkg.QatSeqProd
+    assert q.startQatDevice() == pkg.QZSTD_OK
+    st = q.createSeqProdState()
+    try:
+        for level in (1, 3, 6):
+            seqs = q.generateSequences(st, data, level=level)
+            assert seqs is not None
+            want = np.concatenate([oracle.model_block(data[o:o + BLOCK], level) for o in range(0, len(data), BLOCK)])
+            assert seqs.shape == want.shape and (seqs == want).all()
+            r = oracle.compress_sequences(data, seqs, level=level)
+            assert r["round_trip"]
+            cb = oracle.compress_with_producer(data, q.producer, st, chunk=BLOCK, level=level)
+            assert cb["round_trip"] and cb["errors"] == 0
+            assert 0.95 < r["csize"] / cb["csize"] < 1.01     # one frame instead of one per chunk
+        small = q.generateSequences(st, data[:70000], level=3, block_size=32768)
+        assert small is not None and oracle.compress_sequences(data[:70000], small, level=3)["round_trip"]
+        assert q.generateSequences(st, data, level=13) is None
+    finally:
+        q.freeSeqProdState(st)
+        q.stopQatDevice()
