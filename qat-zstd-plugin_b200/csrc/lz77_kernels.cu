@@ -163,33 +163,48 @@ struct Shared {         // 32-bit shared-window addresses
 //   ringH word, per table: {hash:14 | linked:1 | last:1}   (invalid lanes: linked, not last)
 //   ringC word: {long candidate u16 | short candidate u16 << 16}, 0xFFFF = none / to be filled by T
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_hash(const Shared &S, uint32_t w, uint32_t group, uint32_t lane,
-                                           uint32_t p, uint32_t nh, uint32_t shortMask)
+template <int N>      // N groups per task, interleaved by hand: the MATCH.ANY latencies of all of them overlap
+__device__ __forceinline__ void stage_hash(const Shared &S, uint32_t w, const uint32_t (&group)[N], uint32_t lane,
+                                           uint32_t nh, uint32_t shortMask)
 {
-    const bool valid = p < nh;
-    uint32_t hL = 0, hS = 0;
-    if (valid) {
-        const uint32_t a = S.in + (p & ~3u), sh = (p & 3u) * 8u;
-        const uint32_t w0 = lds32(a), w1 = lds32(a + 4u), w2 = lds32(a + 8u);
-        const uint32_t lo = __funnelshift_r(w0, w1, sh);
-        const uint32_t hi = __funnelshift_r(w1, w2, sh);
-        hL = (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> (32 - kLongBits);
-        hS = (lo * 0x9E3779B1u + (hi & shortMask) * 0xC2B2AE3Du) >> (32 - kShortBits);
+    uint32_t p[N], hL[N], hS[N], w0[N], w1[N], w2[N];
+    bool valid[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        p[i] = w * kWindow + group[i] * 32u + lane;
+        valid[i] = p[i] < nh;
+        const uint32_t a = S.in + (min(p[i], kBlockMax) & ~3u);       // reads stay inside the padded buffer
+        w0[i] = lds32(a); w1[i] = lds32(a + 4u); w2[i] = lds32(a + 8u);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const uint32_t sh = (p[i] & 3u) * 8u;
+        const uint32_t lo = __funnelshift_r(w0[i], w1[i], sh);
+        const uint32_t hi = __funnelshift_r(w1[i], w2[i], sh);
+        hL[i] = (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> (32 - kLongBits);
+        hS[i] = (lo * 0x9E3779B1u + (hi & shortMask) * 0xC2B2AE3Du) >> (32 - kShortBits);
+    }
+    uint32_t mL[N], mS[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {    // invalid lanes get unique keys so they never link
+        mL[i] = __match_any_sync(0xFFFFFFFFu, valid[i] ? hL[i] : (0x10000u | lane));
+        mS[i] = __match_any_sync(0xFFFFFFFFu, valid[i] ? hS[i] : (0x10000u | lane));
     }
     const uint32_t ltMask = (1u << lane) - 1u;
     const uint32_t geMask = ~((2u << lane) - 1u);      // lanes strictly above
-    // invalid lanes get unique keys so they never link
-    const uint32_t mL = __match_any_sync(0xFFFFFFFFu, valid ? hL : (0x10000u | lane));
-    const uint32_t mS = __match_any_sync(0xFFFFFFFFu, valid ? hS : (0x10000u | lane));
-    const uint32_t bL = mL & ltMask, bS = mS & ltMask;
-    // nearest earlier lane with the same hash -> candidate position >> 1
-    const uint32_t cL = bL ? (p - lane + (31u - __clz(bL))) >> 1 : 0xFFFFu;
-    const uint32_t cS = bS ? (p - lane + (31u - __clz(bS))) >> 1 : 0xFFFFu;
-    const uint32_t linkedL = (bL != 0u) || !valid, linkedS = (bS != 0u) || !valid;
-    const uint32_t lastL = valid && (mL & geMask) == 0u, lastS = valid && (mS & geMask) == 0u;
-    const uint32_t ri = ring_byte(group, lane);
-    sts32(S.ringH + (w & 1u) * (kWindow * 4u) + ri, (hL | (linkedL << 14) | (lastL << 15)) | ((hS | (linkedS << 14) | (lastS << 15)) << 16));
-    sts32(S.ringC + (w & (kRingC - 1)) * (kWindow * 4u) + ri, cL | (cS << 16));
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const uint32_t bL = mL[i] & ltMask, bS = mS[i] & ltMask;
+        // nearest earlier lane with the same hash -> candidate position >> 1
+        const uint32_t cL = bL ? (p[i] - lane + (31u - __clz(bL))) >> 1 : 0xFFFFu;
+        const uint32_t cS = bS ? (p[i] - lane + (31u - __clz(bS))) >> 1 : 0xFFFFu;
+        const uint32_t linkedL = (bL != 0u) || !valid[i], linkedS = (bS != 0u) || !valid[i];
+        const uint32_t lastL = valid[i] && (mL[i] & geMask) == 0u, lastS = valid[i] && (mS[i] & geMask) == 0u;
+        const uint32_t vL = valid[i] ? hL[i] : 0u, vS = valid[i] ? hS[i] : 0u;
+        const uint32_t ri = ring_byte(group[i], lane);
+        sts32(S.ringH + (w & 1u) * (kWindow * 4u) + ri, (vL | (linkedL << 14) | (lastL << 15)) | ((vS | (linkedS << 14) | (lastS << 15)) << 16));
+        sts32(S.ringC + (w & (kRingC - 1)) * (kWindow * 4u) + ri, cL | (cS << 16));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -583,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
             sts8(S.in + bulk + tid - 32, gsrc[bulk + tid - 32]);
         for (uint32_t i = tid; i < (kSmemTabL + kSmemTabS) / 16; i += kThreads)    // tabL and tabS are contiguous
             sts128(S.tabL + i * 16u, 0xFFFFFFFFu);
-        if (tid < 2) sts32(S.task + tid * 4u, 0u);
+        if (tid < 2) sts32(S.task + tid * 4u, kEhWarps);
         __syncthreads();
 
         const uint32_t nh = n >= 8 ? n - 7 : 0;
@@ -592,9 +607,13 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         uint32_t cursor = 0;                   // P1: first position the parser has not consumed yet
         EmitCarry ec = {0, 0, 0};              // P2
 
+#ifdef B200SP_ROLE_PROFILE
         unsigned long long busy = 0, blockStart = clock64();
+#endif
         for (uint32_t t = 0; t < nW + 4; t++) {
+#ifdef B200SP_ROLE_PROFILE
             const unsigned long long c0 = clock64();
+#endif
             if (role == 0u) {
                 // bytes this stage may touch: hashing window t reads < (t+1)*1024 + 11, extending
                 // window t-2 reads < (t-1)*1024 + extCap + 36 + 3
@@ -604,17 +623,19 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 // One task queue per stage, heaviest first: the extension groups of window t-2, then the
                 // hash groups of window t.
                 const uint32_t nE = (t >= 2 && t - 2 < nW) ? kGroups : 0u;
-                const uint32_t nAll = nE + (t < nW ? kGroups : 0u);
+                const uint32_t nAll = nE + (t < nW ? kGroups / kHashGroups : 0u);
                 const uint32_t ctr = S.task + (t & 1u) * 4u;
-                for (;;) {
-                    const uint32_t id = pop_task(ctr, lane);
-                    if (id >= nAll) break;
+                // the first task of every pool warp is its own index (the counter starts at kEhWarps); only the
+                // later ones cost an atomic
+                for (uint32_t id = warp; id < nAll; id = pop_task(ctr, lane)) {
                     if (id < nE) {
                         const uint32_t wdx = t - 2;
                         stage_extend(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap);
                     } else {
-                        const uint32_t g = id - nE;
-                        stage_hash(S, t, g, lane, t * kWindow + g * 32u + lane, nh, P.shortMask);
+                        uint32_t gs[kHashGroups];
+#pragma unroll
+                        for (uint32_t i = 0; i < kHashGroups; i++) gs[i] = id - nE + i * (kGroups / kHashGroups);
+                        stage_hash<kHashGroups>(S, t, gs, lane, nh, P.shortMask);
                     }
                 }
             } else if (role == 1u) {
@@ -622,19 +643,23 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
             } else if (role == 2u) {
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabS, 1u, t - 1, lane);
             } else if (role == 3u) {
-                if (lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, 0u);   // next stage's queue (nobody touches it now)
+                if (lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, kEhWarps);   // next stage's queue (nobody touches it now)
                 if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, lane, cursor, P.minMatch, P.lazyDepth);
             } else {
                 if (t >= 4) stage_emit(S, t - 4, lane, ec, out);
             }
+#ifdef B200SP_ROLE_PROFILE
             busy += clock64() - c0;
+#endif
             __syncthreads();
         }
 
+#ifdef B200SP_ROLE_PROFILE          // developer builds only (tools/ab_build.sh NAME -DB200SP_ROLE_PROFILE)
         if (P.roleCycles && lane == 0) {
             atomicAdd(&P.roleCycles[role], busy);
             if (role == 4u) { atomicAdd(&P.roleCycles[5], clock64() - blockStart); atomicAdd(&P.roleCycles[6], (unsigned long long)(nW + 4)); }
         }
+#endif
         if (role == 4u && lane == 0) {
             out[ec.nOut] = make_uint4(0u, n - ec.anchor, 0u, 0u);   // trailing literals / block delimiter
             P.counts[b] = ec.nOut + 1u;

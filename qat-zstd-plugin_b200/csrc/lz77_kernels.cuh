@@ -18,6 +18,10 @@ constexpr uint32_t kGroups        = kWindow / 32;
 constexpr uint32_t kRingC         = 4;          // candidate/match ring: windows in flight between hash and entries
 constexpr uint32_t kLongBits      = 14;
 constexpr uint32_t kShortBits     = 14;
+#ifndef B200SP_HASH_GROUPS
+#define B200SP_HASH_GROUPS 1
+#endif
+constexpr uint32_t kHashGroups    = B200SP_HASH_GROUPS;   // groups per hash task (their MATCH.ANY latencies overlap)
 constexpr uint32_t kProbe         = 16;         // bytes compared per candidate before a winner is picked
 constexpr uint32_t kMaxExtCap     = 256;
 constexpr uint32_t kInputPad      = 320;        // readable slack after the block in shared memory

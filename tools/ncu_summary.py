@@ -40,19 +40,27 @@ def main():
     both = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(both)))
     hdr2 = rows[2]
-    iL, iS, iI = hdr2.index("Line No"), hdr2.index("# Samples"), hdr2.index("Instructions Executed")
+    iL, iS, iI, iA = hdr2.index("Line No"), hdr2.index("# Samples"), hdr2.index("Instructions Executed"), hdr2.index("Address")
     src = open(SRC).read().split("\n")
     marks = sorted((i, l.split("(")[0].split()[-1]) for i, l in enumerate(src, 1)
                    if (l.startswith("__device__") or l.startswith("__global__")) and "(" in l)
-    agg, ti, ts = {}, 0, 0
+    # every CUDA line is followed by the SASS rows it produced; count each SASS address once and
+    # attribute it to the function whose definition precedes that line
+    agg, ti, ts, cur, seen = {}, 0, 0, None, set()
     for r in rows[3:]:
-        if len(r) <= iI or not r[iL].isdigit():
+        if len(r) <= iI:
             continue
+        if r[iL].isdigit():
+            cur = int(r[iL])
+            continue
+        if cur is None or r[iA] in seen:
+            continue
+        seen.add(r[iA])
         try:
             ins, smp = int(r[iI]), int(r[iS])
         except ValueError:
             continue
-        k = bisect.bisect_right([x[0] for x in marks], int(r[iL])) - 1
+        k = bisect.bisect_right([x[0] for x in marks], cur) - 1
         name = marks[k][1] if k >= 0 else "helpers"
         a = agg.setdefault(name, [0, 0])
         a[0] += ins
