@@ -41,43 +41,31 @@ bool device_usable(int dev)
 }
 
 // ---- wire format: offset | litLength << 17 | matchLength << 35 ----------------------------
-__global__ void scan_counts_kernel(const uint32_t *__restrict__ counts, uint32_t nBlocks,
-                                   unsigned long long *__restrict__ offsets)
+// The post-processing kernels of chunk k run while the parser CTAs of chunk k+1 own every SM (1024 threads
+// x 60 registers): they are sized (128 threads, <= 32 registers) to fit beside one parser CTA.
+constexpr int kPostThreads = 128;
+
+__global__ void __launch_bounds__(32) scan_counts_kernel(const uint32_t *__restrict__ counts, uint32_t nBlocks,
+                                                         unsigned long long *__restrict__ offsets)
 {
-    // single CTA: chunked exclusive scan, enough for a few hundred thousand blocks
-    __shared__ unsigned long long warpSums[32];
-    __shared__ unsigned long long running;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) running = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < nBlocks; base += blockDim.x) {
-        const uint32_t i = base + tid;
-        unsigned long long v = i < nBlocks ? counts[i] : 0, incl = v;
+    // one warp, shuffles only: no shared memory, so the CTA fits in the ~1 KB the parser leaves free on an SM
+    const uint32_t lane = threadIdx.x;
+    unsigned long long running = 0;
+    for (uint32_t base = 0; base < nBlocks; base += 32) {
+        const uint32_t i = base + lane;
+        const unsigned long long v = i < nBlocks ? counts[i] : 0;
+        unsigned long long incl = v;
         for (int d = 1; d < 32; d <<= 1) {
-            unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= (uint32_t)d) incl += o;
         }
-        if (lane == 31) warpSums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = lane < (blockDim.x >> 5) ? warpSums[lane] : 0, wi = w;
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-                if (lane >= (uint32_t)d) wi += o;
-            }
-            warpSums[lane] = wi - w;      // exclusive
-        }
-        __syncthreads();
-        const unsigned long long excl = running + warpSums[warp] + incl - v;
-        if (i < nBlocks) offsets[i] = excl;
-        __syncthreads();
-        if (tid == blockDim.x - 1) running = excl + v;
-        __syncthreads();
+        if (i < nBlocks) offsets[i] = running + incl - v;
+        running += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
-    if (tid == 0) offsets[nBlocks] = running;
+    if (lane == 0) offsets[nBlocks] = running;
 }
 
-__global__ void pack_kernel(const uint4 *__restrict__ seqs, uint64_t seqStride,
+__global__ void __launch_bounds__(kPostThreads) pack_kernel(const uint4 *__restrict__ seqs, uint64_t seqStride,
                             const uint32_t *__restrict__ counts,
                             const unsigned long long *__restrict__ offsets, uint32_t nBlocks,
                             unsigned long long *__restrict__ packed)
@@ -180,8 +168,11 @@ struct b200sp_engine {
     int numSMs;
     cudaStream_t stream;         // compute
     cudaStream_t sIn, sOut;      // host->device / device->host copies of the pipelined host path
-    cudaEvent_t evIn[kMaxChunks], evDone[kMaxChunks];
-    unsigned int *d_work;        // dynamic scheduler counter
+    cudaStream_t sParse[2];      // parser launches of consecutive chunks alternate: chunk k+1's CTAs move in as chunk k's retire
+    cudaStream_t sPost;          // scan + pack + small D2H of finished chunks (high priority, co-resident with the parser)
+    cudaEvent_t evIn[kMaxChunks], evParsed[kMaxChunks], evDone[kMaxChunks];
+    unsigned int *d_work;        // dynamic scheduler counter (+ developer role counters)
+    unsigned int *d_chunkWork;   // [kMaxChunks] scheduler counters of the pipelined host path
     // host-path scratch (grown on demand)
     uint8_t *d_src;      size_t d_srcCap;
     uint4 *d_seqs;       size_t d_seqsCap;      // entries
@@ -237,12 +228,21 @@ int b200sp_engine_create(int device, b200sp_engine **out)
     ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->sIn, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->sOut, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->sParse[0], cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->sParse[1], cudaStreamNonBlocking);
+    if (ce == cudaSuccess) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        ce = cudaStreamCreateWithPriority(&e->sPost, cudaStreamNonBlocking, hi);
+    }
     for (int k = 0; k < kMaxChunks && ce == cudaSuccess; k++) {
         ce = cudaEventCreateWithFlags(&e->evIn[k], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->evParsed[k], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->evDone[k], cudaEventDisableTiming);
     }
     if (ce == cudaSuccess) ce = cudaMalloc(&e->d_work, 256);
     if (ce == cudaSuccess) ce = cudaMemset(e->d_work, 0, 256);
+    if (ce == cudaSuccess) ce = cudaMalloc(&e->d_chunkWork, kMaxChunks * sizeof(unsigned int));
     if (ce != cudaSuccess) { b200sp_engine_destroy(e); return fail(B200SP_ECUDA, "engine_create", ce); }
     *out = e;
     return B200SP_OK;
@@ -255,7 +255,14 @@ void b200sp_engine_destroy(b200sp_engine *e)
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
     if (e->sIn) cudaStreamDestroy(e->sIn);
     if (e->sOut) { cudaStreamSynchronize(e->sOut); cudaStreamDestroy(e->sOut); }
-    for (int k = 0; k < kMaxChunks; k++) { if (e->evIn[k]) cudaEventDestroy(e->evIn[k]); if (e->evDone[k]) cudaEventDestroy(e->evDone[k]); }
+    for (int i = 0; i < 2; i++) if (e->sParse[i]) { cudaStreamSynchronize(e->sParse[i]); cudaStreamDestroy(e->sParse[i]); }
+    if (e->sPost) { cudaStreamSynchronize(e->sPost); cudaStreamDestroy(e->sPost); }
+    for (int k = 0; k < kMaxChunks; k++) {
+        if (e->evIn[k]) cudaEventDestroy(e->evIn[k]);
+        if (e->evParsed[k]) cudaEventDestroy(e->evParsed[k]);
+        if (e->evDone[k]) cudaEventDestroy(e->evDone[k]);
+    }
+    cudaFree(e->d_chunkWork);
     free(e->h_goffsets);
     cudaFree(e->d_work); cudaFree(e->d_src); cudaFree(e->d_seqs); cudaFree(e->d_counts);
     cudaFree(e->d_offsets); cudaFree(e->d_packed);
@@ -280,9 +287,10 @@ static int check_batch(const void *d_src, uint32_t blockSize, uint64_t stride, c
     return B200SP_OK;
 }
 
-int b200sp_parse_device(b200sp_engine *e, const void *d_src, uint64_t totalSize, uint32_t blockSize,
+static int launch_batch(b200sp_engine *e, const void *d_src, uint64_t totalSize, uint32_t blockSize,
                         uint64_t stride, const uint32_t *d_sizes, uint32_t nBlocks, int level,
-                        b200sp_sequence *d_seqs, uint64_t seqStride, uint32_t *d_counts, void *cudaStream)
+                        b200sp_sequence *d_seqs, uint64_t seqStride, uint32_t *d_counts, cudaStream_t st,
+                        unsigned int *workCounter)
 {
     if (!e) return fail(B200SP_EINVAL, "null engine");
     b200sp::ParseParams p;
@@ -292,7 +300,6 @@ int b200sp_parse_device(b200sp_engine *e, const void *d_src, uint64_t totalSize,
     if (rc) return rc;
     if (nBlocks == 0) return B200SP_OK;
     if (!d_seqs || !d_counts) return fail(B200SP_EINVAL, "null output");
-    cudaStream_t st = cudaStream ? static_cast<cudaStream_t>(cudaStream) : e->stream;
     CU_TRY(cudaSetDevice(e->device), "cudaSetDevice");
     p.src = static_cast<const uint8_t *>(d_src);
     p.stride = stride;
@@ -303,13 +310,23 @@ int b200sp_parse_device(b200sp_engine *e, const void *d_src, uint64_t totalSize,
     p.seqs = reinterpret_cast<uint4 *>(d_seqs);
     p.seqStride = seqStride;
     p.counts = d_counts;
-    p.workCounter = e->d_work;
+    p.workCounter = workCounter;
     // developer profiling: B200SP_ROLE_PROFILE=1 accumulates per-role busy cycles in d_work[8..]
     static const bool roleProfile = getenv("B200SP_ROLE_PROFILE") != nullptr;
     p.roleCycles = roleProfile ? reinterpret_cast<unsigned long long *>(e->d_work) + 1 : nullptr;
-    CU_TRY(cudaMemsetAsync(e->d_work, 0, sizeof(unsigned int), st), "cudaMemsetAsync(work counter)");
+    CU_TRY(cudaMemsetAsync(workCounter, 0, sizeof(unsigned int), st), "cudaMemsetAsync(work counter)");
     CU_TRY(b200sp::launch_parse(p, e->numSMs, st), "launch lz77_parse_kernel");
     return B200SP_OK;
+}
+
+int b200sp_parse_device(b200sp_engine *e, const void *d_src, uint64_t totalSize, uint32_t blockSize,
+                        uint64_t stride, const uint32_t *d_sizes, uint32_t nBlocks, int level,
+                        b200sp_sequence *d_seqs, uint64_t seqStride, uint32_t *d_counts, void *cudaStream)
+{
+    if (!e) return fail(B200SP_EINVAL, "null engine");
+    cudaStream_t st = cudaStream ? static_cast<cudaStream_t>(cudaStream) : e->stream;
+    return launch_batch(e, d_src, totalSize, blockSize, stride, d_sizes, nBlocks, level, d_seqs, seqStride, d_counts, st,
+                        e->d_work);
 }
 
 int b200sp_verify_device(b200sp_engine *e, const void *d_src, uint64_t totalSize, uint32_t blockSize,
@@ -369,16 +386,19 @@ int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint3
     const size_t perBlockWorst = static_cast<size_t>(blockSize) / 4 + 2;   // entries
     const size_t devBytes = nBlocks * stride + 16;
 
-    // ---- chunk plan: the copies of chunk k+1 / k-1 overlap the kernels of chunk k.  The first chunk
-    // is one wave of blocks (so the SMs start early), later chunks three waves (small launch tails).
+    // ---- chunk plan: the copies of chunk k+1 / k-1 overlap the kernels of chunk k, and the parser launches
+    // of consecutive chunks sit on two streams, so the CTAs of chunk k+1 move onto the SMs as those of chunk
+    // k retire (no idle tail per chunk).  The first chunk is a quarter wave (the first SMs start after a 5 MB
+    // copy), the second fills the wave, later chunks are one wave each (more when there are many blocks).
     const size_t sms = static_cast<size_t>(e->numSMs);
-    size_t big = 3 * sms;
-    if (nBlocks > sms + big * (kMaxChunks - 1)) big = ((nBlocks - sms + kMaxChunks - 2) / (kMaxChunks - 1) + sms - 1) / sms * sms;
+    const size_t first = sms / 4 ? sms / 4 : 1;
+    size_t big = sms;
+    if (nBlocks > sms + big * (kMaxChunks - 2)) big = ((nBlocks - sms + kMaxChunks - 3) / (kMaxChunks - 2) + sms - 1) / sms * sms;
     size_t chunkStart[kMaxChunks + 1];
     int nChunks = 0;
     for (size_t b = 0; b < nBlocks;) {
         chunkStart[nChunks++] = b;
-        b += (nChunks == 1 && nBlocks > sms) ? sms : big;
+        b += nChunks == 1 ? first : nChunks == 2 ? sms - first : big;
     }
     chunkStart[nChunks] = nBlocks;
 
@@ -427,7 +447,8 @@ int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint3
             if (rem) CU_TRY(cudaMemcpyAsync(dsrc + full * stride, hsrc + full * blockSize, rem, cudaMemcpyHostToDevice, e->sIn), "H2D tail");
         }
         CU_TRY(cudaEventRecord(e->evIn[k], e->sIn), "event record");
-        CU_TRY(cudaStreamWaitEvent(e->stream, e->evIn[k], 0), "stream wait");
+        cudaStream_t sp = e->sParse[k & 1];
+        CU_TRY(cudaStreamWaitEvent(sp, e->evIn[k], 0), "stream wait");
 
         // sizes in the strided layout: the last block of the chunk holds what is left of the input
         const uint64_t lastBytes = (byte1 - byte0) - (nb - 1) * static_cast<size_t>(blockSize);
@@ -435,17 +456,19 @@ int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint3
         uint4 *dseqs = e->d_seqs + b0 * seqStride;
         uint32_t *dcounts = e->d_counts + b0;
         unsigned long long *doffs = e->d_offsets + b0 + k;
-        int rc = b200sp_parse_device(e, dsrc, totalStrided, blockSize, stride, nullptr, static_cast<uint32_t>(nb), level,
-                                     reinterpret_cast<b200sp_sequence *>(dseqs), seqStride, dcounts, nullptr);
+        int rc = launch_batch(e, dsrc, totalStrided, blockSize, stride, nullptr, static_cast<uint32_t>(nb), level,
+                              reinterpret_cast<b200sp_sequence *>(dseqs), seqStride, dcounts, sp, e->d_chunkWork + k);
         if (rc) return rc;
-        scan_counts_kernel<<<1, 1024, 0, e->stream>>>(dcounts, static_cast<uint32_t>(nb), doffs);
+        CU_TRY(cudaEventRecord(e->evParsed[k], sp), "event record");
+        CU_TRY(cudaStreamWaitEvent(e->sPost, e->evParsed[k], 0), "stream wait");
+        scan_counts_kernel<<<1, 32, 0, e->sPost>>>(dcounts, static_cast<uint32_t>(nb), doffs);
         CU_TRY(cudaGetLastError(), "launch scan_counts_kernel");
-        pack_kernel<<<e->numSMs * 8, 256, 0, e->stream>>>(dseqs, seqStride, dcounts, doffs, static_cast<uint32_t>(nb),
-                                                         e->d_packed + b0 * perBlockWorst);
+        pack_kernel<<<e->numSMs * 2, kPostThreads, 0, e->sPost>>>(dseqs, seqStride, dcounts, doffs, static_cast<uint32_t>(nb),
+                                                                 e->d_packed + b0 * perBlockWorst);
         CU_TRY(cudaGetLastError(), "launch pack_kernel");
-        CU_TRY(cudaMemcpyAsync(e->h_counts + b0, dcounts, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream), "D2H counts");
-        CU_TRY(cudaMemcpyAsync(e->h_offsets + b0 + k, doffs, (nb + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream), "D2H offsets");
-        CU_TRY(cudaEventRecord(e->evDone[k], e->stream), "event record");
+        CU_TRY(cudaMemcpyAsync(e->h_counts + b0, dcounts, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->sPost), "D2H counts");
+        CU_TRY(cudaMemcpyAsync(e->h_offsets + b0 + k, doffs, (nb + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->sPost), "D2H offsets");
+        CU_TRY(cudaEventRecord(e->evDone[k], e->sPost), "event record");
     }
 
     // ---- drain: as each chunk completes, fetch exactly its packed entries on the copy-out stream
