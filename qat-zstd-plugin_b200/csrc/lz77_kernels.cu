@@ -88,6 +88,15 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
     return v;
 }
+// Same load, but free to be scheduled (not ordered against the other asm statements): only for words that
+// cannot change while the calling task runs - the staged block, ring words written in earlier stages - and
+// whose address depends on the task index (so it cannot move above the pop / the stage barrier).
+__device__ __forceinline__ uint32_t ldsc32(uint32_t a)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds16(uint32_t a)
 {
     uint32_t v;
@@ -115,7 +124,7 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t v)
 __device__ __forceinline__ uint32_t ld32u(uint32_t in, uint32_t bytePos)
 {
     const uint32_t a = in + (bytePos & ~3u);
-    return __funnelshift_r(lds32(a), lds32(a + 4u), (bytePos & 3u) * 8u);
+    return __funnelshift_r(ldsc32(a), ldsc32(a + 4u), (bytePos & 3u) * 8u);
 }
 
 // Warp-uniform pop from a shared-memory task counter: one ATOMS by lane 0, one broadcast.
@@ -174,7 +183,7 @@ __device__ __forceinline__ void stage_hash(const Shared &S, uint32_t w, const ui
         p[i] = w * kWindow + group[i] * 32u + lane;
         valid[i] = p[i] < nh;
         const uint32_t a = S.in + (min(p[i], kBlockMax) & ~3u);       // reads stay inside the padded buffer
-        w0[i] = lds32(a); w1[i] = lds32(a + 4u); w2[i] = lds32(a + 8u);
+        w0[i] = ldsc32(a); w1[i] = ldsc32(a + 4u); w2[i] = ldsc32(a + 8u);
     }
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -250,13 +259,15 @@ __device__ __forceinline__ uint32_t first_diff_16(uint32_t x1, uint32_t x2, uint
     return len;
 }
 
+template <bool kFuseHash>
 __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32_t group, uint32_t lane,
                                              uint32_t p, uint32_t n, uint32_t nh, uint32_t minMatch,
-                                             uint32_t extCap)
+                                             uint32_t extCap, uint32_t hashWindow = 0, uint32_t hashNh = 0,
+                                             uint32_t shortMask = 0)
 {
     const uint32_t slot = w & (kRingC - 1);
     const uint32_t idx = S.ringC + slot * (kWindow * 4u) + ring_byte(group, lane);
-    const uint32_t cw = lds32(idx);
+    const uint32_t cw = ldsc32(idx);
     const uint32_t cL = cw & 0xFFFFu, cS = cw >> 16;
     const uint32_t in = S.in;
     const bool valid = p < nh;
@@ -267,18 +278,30 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32
     uint32_t a0, a1, a2, a3;
     {
         const uint32_t a = in + (min(p, kBlockMax) & ~3u), sh = (p & 3u) * 8u;
-        const uint32_t x0 = lds32(a), x1 = lds32(a + 4u), x2 = lds32(a + 8u), x3 = lds32(a + 12u), x4 = lds32(a + 16u);
+        const uint32_t x0 = ldsc32(a), x1 = ldsc32(a + 4u), x2 = ldsc32(a + 8u), x3 = ldsc32(a + 12u), x4 = ldsc32(a + 16u);
         a0 = __funnelshift_r(x0, x1, sh); a1 = __funnelshift_r(x1, x2, sh);
         a2 = __funnelshift_r(x2, x3, sh); a3 = __funnelshift_r(x3, x4, sh);
+    }
+    // both candidates' first 20 bytes: the slot stands for positions 2c and 2c+1 (same 32-bit word row)
+    uint32_t yy[2][5];
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const uint32_t a = in + (min(2u * (t ? cS : cL), kBlockMax) & ~3u);
+#pragma unroll
+        for (int k = 0; k < 5; k++) yy[t][k] = ldsc32(a + 4u * k);
+    }
+    if (kFuseHash) {        // same basic block as the probe: the MATCH.ANY latency hides behind the loads above
+        const uint32_t gs[1] = {group};
+        stage_hash<1>(S, hashWindow, gs, lane, hashNh, shortMask);
     }
 #pragma unroll
     for (int t = 0; t < 2; t++) {
         const uint32_t c = t ? cS : cL;
-        // the slot stands for positions 2c and 2c+1 (same 32-bit word row): pick the one whose first
-        // 4 bytes equal ours, the nearer one if both do.  0xFFFF (empty) fails q0 < p by construction.
+        // pick the one of 2c, 2c+1 whose first 4 bytes equal ours, the nearer one if both do.
+        // 0xFFFF (empty) fails q0 < p by construction.
         const uint32_t q0 = 2u * c;
-        const uint32_t a = in + (min(q0, kBlockMax) & ~3u), sh0 = (q0 & 3u) * 8u;   // q0 even: sh0 is 0 or 16
-        const uint32_t y0 = lds32(a), y1 = lds32(a + 4u), y2 = lds32(a + 8u), y3 = lds32(a + 12u), y4 = lds32(a + 16u);
+        const uint32_t sh0 = (q0 & 3u) * 8u;   // q0 even: sh0 is 0 or 16
+        const uint32_t y0 = yy[t][0], y1 = yy[t][1], y2 = yy[t][2], y3 = yy[t][3], y4 = yy[t][4];
         const bool c0 = valid && q0 < p && __funnelshift_r(y0, y1, sh0) == a0;
         const bool c1 = valid && q0 + 1u < p && __funnelshift_r(y0, y1, sh0 + 8u) == a0;
         const uint32_t sh = sh0 + (c1 ? 8u : 0u);
@@ -623,14 +646,24 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 // One task queue per stage, heaviest first: the extension groups of window t-2, then the
                 // hash groups of window t.
                 const uint32_t nE = (t >= 2 && t - 2 < nW) ? kGroups : 0u;
+#ifdef B200SP_FUSED_TASKS      // hash tasks only while there is no extension work yet (the first two stages)
+                const uint32_t nAll = nE ? nE : (t < nW ? kGroups / kHashGroups : 0u);
+#else
                 const uint32_t nAll = nE + (t < nW ? kGroups / kHashGroups : 0u);
+#endif
                 const uint32_t ctr = S.task + (t & 1u) * 4u;
                 // the first task of every pool warp is its own index (the counter starts at kEhWarps); only the
                 // later ones cost an atomic
                 for (uint32_t id = warp; id < nAll; id = pop_task(ctr, lane)) {
                     if (id < nE) {
                         const uint32_t wdx = t - 2;
-                        stage_extend(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap);
+#ifdef B200SP_FUSED_TASKS
+                        // past the last window the fused hash runs with no valid position (harmless ring writes)
+                        stage_extend<true>(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap,
+                                           t, t < nW ? nh : 0u, P.shortMask);
+#else
+                        stage_extend<false>(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap);
+#endif
                     } else {
                         uint32_t gs[kHashGroups];
 #pragma unroll
