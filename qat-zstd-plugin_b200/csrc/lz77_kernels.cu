@@ -163,7 +163,6 @@ struct Shared {         // 32-bit shared-window addresses
     uint32_t entA;      // u32[2][kGroups]      P1 -> P2: position at which the parse enters each group
     uint32_t mbar;      // u64[kTmaChunks]
     uint32_t work;      // next block index
-    uint32_t task;      // u32[2] per-stage task counters of the hash/extend warps (double-buffered)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -229,7 +228,8 @@ __device__ __forceinline__ void stage_table(const Shared &S, uint32_t tab, uint3
     for (uint32_t g0 = 0; g0 < kGroups; g0 += 8) {
         uint32_t hw[8], tv[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) hw[k] = (lds32(rh + ring_byte(g0 + k, lane)) >> sh) & 0xFFFFu;
+        for (int k = 0; k < 8; k++)      // groups past the window's end: linked, not last -> no table access below
+            hw[k] = g0 + k < kGroups ? (lds32(rh + ring_byte(g0 + k, lane)) >> sh) & 0xFFFFu : 0x4000u;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const uint32_t ha = tab + (hw[k] & 0x3FFFu) * 2u;
@@ -355,7 +355,7 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32
     }
     sts32(idx, pk);                                      // prefix-max within the group
     const uint32_t own = __ballot_sync(0xFFFFFFFFu, (pk >> 23) >= lane + minMatch);
-    if (lane == 31) { sts32(S.gmax + (slot * kGroups + group) * 4u, pk); sts32(S.gown + (slot * kGroups + group) * 4u, own); }
+    if (lane == 31) { sts32(S.gmax + (slot * 32u + group) * 4u, pk); sts32(S.gown + (slot * 32u + group) * 4u, own); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -402,14 +402,15 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
         uint32_t sl = slot;
         bool ok = true;
         if (gg < 0) { ok = w > 0; gg += kGroups; sl = (w - 1) & (kRingC - 1); }
-        const uint32_t v = ok ? lds32(S.gmax + (sl * kGroups + gg) * 4u) : 0u;
+        const uint32_t v = ok ? lds32(S.gmax + (sl * 32u + gg) * 4u) : 0u;
         const uint32_t rel = v >> 23;
         if (rel > 32u * k) c = max(c, ((rel - 32u * k) << 23) | ((32u + k) << 17) | (v & 0x1FFFFu));
     }
     const uint32_t cRel = c >> 23;
     uint32_t cover = 0;
     if (cRel >= minMatch) cover = (cRel - minMatch >= 31u) ? 0xFFFFFFFFu : (2u << (cRel - minMatch)) - 1u;
-    const uint32_t has = lds32(S.gown + (slot * kGroups + lane) * 4u) | cover;
+    const bool act = lane < kGroups;                    // lanes beyond the window's last group stay inert
+    const uint32_t has = act ? lds32(S.gown + (slot * 32u + lane) * 4u) | cover : 0u;
     const uint32_t segStart = base + lane * 32u, segEnd = segStart + 32u;
 
     // ---- every lane guesses that the parser enters its group at its first position; the guesses are
@@ -420,6 +421,7 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
     // First guess: the parse arrives through the carried match (the farthest-reaching one usually is the
     // one the previous groups ended with); any guess converges to the same fixed point.
     uint32_t entry = lane == 0 ? max(cursor, base) : segStart + min(cRel, 32u);
+    if (!act) entry = 0xFFFFFFFFu;                      // never live, never changes
     uint32_t visited = 0, pm = 0, walked = 0xFFFFFFFFu, exitPos = 0;
     for (;;) {
         if (entry != walked) {                   // a lane whose entry did not change keeps its exit
@@ -449,14 +451,14 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
             if (lane >= static_cast<uint32_t>(d)) pm = max(pm, o);
         }
         const uint32_t prevMax = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
-        const uint32_t want = lane == 0 ? entry : max(prevMax, segStart);
+        const uint32_t want = (lane == 0 || !act) ? entry : max(prevMax, segStart);
         const bool changed = want != entry;
         entry = want;
         if (!__any_sync(0xFFFFFFFFu, changed)) break;
     }
     cursor = max(__shfl_sync(0xFFFFFFFFu, pm, 31), base + kWindow);
-    sts32(S.hasA + ((w & 1u) * kGroups + lane) * 4u, has);
-    sts32(S.entA + ((w & 1u) * kGroups + lane) * 4u, entry);
+    sts32(S.hasA + ((w & 1u) * 32u + lane) * 4u, has);
+    sts32(S.entA + ((w & 1u) * 32u + lane) * 4u, entry);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -472,8 +474,8 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
 {
     const uint32_t base = w * kWindow;
     const uint32_t linkRow = S.ringL + (w & 1u) * (kWindow * 4u);
-    const uint32_t has = lds32(S.hasA + ((w & 1u) * kGroups + lane) * 4u);
-    const uint32_t entry = lds32(S.entA + ((w & 1u) * kGroups + lane) * 4u);
+    const uint32_t has = lds32(S.hasA + ((w & 1u) * 32u + lane) * 4u);
+    const uint32_t entry = lds32(S.entA + ((w & 1u) * 32u + lane) * 4u);
     const uint32_t segStart = base + lane * 32u, segEnd = segStart + 32u;
     const uint32_t cur0 = entry < segEnd ? entry - segStart : 32u;
 
@@ -568,13 +570,12 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         S.ringH = p; p += kSmemRingH;
         S.ringC = p; p += kSmemRingC;
         S.ringL = p; p += kSmemRingL;
-        S.gmax = p;  p += kRingC * kGroups * 4;
-        S.gown = p;  p += kRingC * kGroups * 4;
-        S.hasA = p;  p += 2 * kGroups * 4;
-        S.entA = p;  p += 2 * kGroups * 4;
+        S.gmax = p;  p += kRingC * 32 * 4;
+        S.gown = p;  p += kRingC * 32 * 4;
+        S.hasA = p;  p += 2 * 32 * 4;
+        S.entA = p;  p += 2 * 32 * 4;
         S.mbar = p;  p += kTmaChunks * 8;
-        S.work = p;  p += 8;
-        S.task = p;
+        S.work = p;
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // Role of this warp: 0 = hash/extend pool, 1 = long table, 2 = short table, 3 = entries (P1), 4 = emit (P2).
@@ -621,7 +622,6 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
             sts8(S.in + bulk + tid - 32, gsrc[bulk + tid - 32]);
         for (uint32_t i = tid; i < (kSmemTabL + kSmemTabS) / 16; i += kThreads)    // tabL and tabS are contiguous
             sts128(S.tabL + i * 16u, 0xFFFFFFFFu);
-        if (tid < 2) sts32(S.task + tid * 4u, kEhWarps);
         __syncthreads();
 
         const uint32_t nh = n >= 8 ? n - 7 : 0;
@@ -643,40 +643,22 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 const uint32_t need = min(bulk, (t + 1) * kWindow + 16u);
                 const uint32_t wantChunks = (need + kTmaChunk - 1) / kTmaChunk;
                 while (chunksSeen < wantChunks) { mbar_wait(S.mbar + chunksSeen * 8u, (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
-                // One task queue per stage, heaviest first: the extension groups of window t-2, then the
-                // hash groups of window t.
-                const uint32_t nE = (t >= 2 && t - 2 < nW) ? kGroups : 0u;
-#ifdef B200SP_FUSED_TASKS      // hash tasks only while there is no extension work yet (the first two stages)
-                const uint32_t nAll = nE ? nE : (t < nW ? kGroups / kHashGroups : 0u);
-#else
-                const uint32_t nAll = nE + (t < nW ? kGroups / kHashGroups : 0u);
-#endif
-                const uint32_t ctr = S.task + (t & 1u) * 4u;
-                // the first task of every pool warp is its own index (the counter starts at kEhWarps); only the
-                // later ones cost an atomic
-                for (uint32_t id = warp; id < nAll; id = pop_task(ctr, lane)) {
-                    if (id < nE) {
-                        const uint32_t wdx = t - 2;
-#ifdef B200SP_FUSED_TASKS
-                        // past the last window the fused hash runs with no valid position (harmless ring writes)
-                        stage_extend<true>(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap,
-                                           t, t < nW ? nh : 0u, P.shortMask);
-#else
-                        stage_extend<false>(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap);
-#endif
-                    } else {
-                        uint32_t gs[kHashGroups];
-#pragma unroll
-                        for (uint32_t i = 0; i < kHashGroups; i++) gs[i] = id - nE + i * (kGroups / kHashGroups);
-                        stage_hash<kHashGroups>(S, t, gs, lane, nh, P.shortMask);
-                    }
+                // One fused task per pool warp and stage: extend group `warp` of window t-2 and, inside its probe
+                // block, hash group `warp` of window t (the MATCH.ANY latency hides behind the candidate loads).
+                const uint32_t wdx = t - 2;
+                if (t >= 2 && wdx < nW) {
+                    // past the last window the fused hash runs with no valid position (harmless ring writes)
+                    stage_extend<true>(S, wdx, warp, lane, wdx * kWindow + warp * 32u + lane, n, nh, P.minMatch, P.extCap,
+                                       t, t < nW ? nh : 0u, P.shortMask);
+                } else if (t < nW) {
+                    const uint32_t gs[1] = {warp};
+                    stage_hash<1>(S, t, gs, lane, nh, P.shortMask);
                 }
             } else if (role == 1u) {
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabL, 0u, t - 1, lane);
             } else if (role == 2u) {
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabS, 1u, t - 1, lane);
             } else if (role == 3u) {
-                if (lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, kEhWarps);   // next stage's queue (nobody touches it now)
                 if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, lane, cursor, P.minMatch, P.lazyDepth);
             } else {
                 if (t >= 4) stage_emit(S, t - 4, lane, ec, out);

@@ -13,15 +13,17 @@
 namespace b200sp {
 
 constexpr uint32_t kBlockMax      = 1u << 17;   // ZSTD_BLOCKSIZE_MAX
-constexpr uint32_t kWindow        = 1024;       // positions per pipeline window
-constexpr uint32_t kGroups        = kWindow / 32;
+#ifndef B200SP_GROUPS
+#define B200SP_GROUPS 28
+#endif
+// A window is one stage's worth of work: kGroups groups of 32 positions, one per pool warp, so that every
+// pool warp runs exactly one fused task (extend group g of window t-2 + hash group g of window t) per stage:
+// no queue, no atomics, and no warp has to run two tasks back to back while the others wait.
+constexpr uint32_t kGroups        = B200SP_GROUPS;
+constexpr uint32_t kWindow        = kGroups * 32;   // positions per pipeline window
 constexpr uint32_t kRingC         = 4;          // candidate/match ring: windows in flight between hash and entries
 constexpr uint32_t kLongBits      = 14;
 constexpr uint32_t kShortBits     = 14;
-#ifndef B200SP_HASH_GROUPS
-#define B200SP_HASH_GROUPS 1
-#endif
-constexpr uint32_t kHashGroups    = B200SP_HASH_GROUPS;   // groups per hash task (their MATCH.ANY latencies overlap)
 constexpr uint32_t kProbe         = 16;         // bytes compared per candidate before a winner is picked
 constexpr uint32_t kMaxExtCap     = 256;
 constexpr uint32_t kInputPad      = 320;        // readable slack after the block in shared memory
@@ -46,9 +48,11 @@ constexpr uint32_t kSmemTabS    = (1u << kShortBits) * 2;
 constexpr uint32_t kSmemRingH   = 2 * kWindow * 4;        // hash words, H -> T
 constexpr uint32_t kSmemRingC   = kRingC * kWindow * 4;   // candidates -> packed prefix maxima, H/T -> E -> P1
 constexpr uint32_t kSmemRingL   = 2 * kWindow * 4;        // memoised parse decisions, P1 -> P2
-constexpr uint32_t kSmemGroup   = (2 * kRingC + 4) * kGroups * 4;   // gmax, gown, hasA, entA
-constexpr uint32_t kSmemMisc    = 128;          // mbarriers + work-item slot + task counters
+constexpr uint32_t kSmemGroup   = (2 * kRingC + 4) * 32 * 4;   // gmax, gown, hasA, entA (32 entries per window)
+constexpr uint32_t kSmemMisc    = 128;          // mbarriers + work-item slot
 constexpr uint32_t kSmemTotal   = kSmemInput + kSmemTabL + kSmemTabS + kSmemRingH + kSmemRingC + kSmemRingL + kSmemGroup + kSmemMisc;
+static_assert(kGroups == static_cast<uint32_t>(kEhWarps), "one fused task per pool warp and stage");
+static_assert(kGroups >= 9 && kGroups <= 32, "a lane of the parse warps owns one group; carries look 8 groups back");
 static_assert(kSmemTotal <= 232448, "exceeds 227 KB of shared memory per CTA");
 
 struct ParseParams {
