@@ -28,7 +28,7 @@
 #include <string.h>
 
 #define KGRP    32u               /* positions per group (one warp's worth) */
-#define KGPW    28u               /* groups per window = lanes of the parse warps in use (kGroups of the kernel) */
+#define KGPW    26u               /* groups per window = lanes of the parse warps in use (kGroups of the kernel) */
 #define KWIN    (KGPW * KGRP)     /* positions per pipeline window */
 
 static inline uint32_t umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
