@@ -708,6 +708,13 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
             }
 #ifdef B200SP_ROLE_PROFILE
             busy += clock64() - c0;
+            // slowest pool warp of the stage (developer builds): collected in the spare word after curTag
+            if (role == 0u && lane == 0) atomicMax(reinterpret_cast<unsigned int *>(__cvta_shared_to_generic(S.curTag + 4u)), static_cast<unsigned int>(clock64() - c0));
+            if (role == 5u && lane == 0) {      // the pool warps of this stage are still busy: this is last stage's maximum
+                const uint32_t m = lds32(S.curTag + 4u);
+                sts32(S.curTag + 4u, 0u);
+                if (P.roleCycles) atomicAdd(&P.roleCycles[8], static_cast<unsigned long long>(m));
+            }
 #endif
             if (!arrived) {
                 if (t & 1u) asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");

@@ -355,8 +355,8 @@ int b200sp_debug_role_cycles(b200sp_engine *e, unsigned long long *out6)
 {
     if (!e || !out6) return B200SP_EINVAL;
     cudaStreamSynchronize(e->stream);
-    cudaMemcpy(out6, reinterpret_cast<unsigned long long *>(e->d_work) + 1, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    cudaMemset(reinterpret_cast<unsigned long long *>(e->d_work) + 1, 0, 8 * sizeof(unsigned long long));
+    cudaMemcpy(out6, reinterpret_cast<unsigned long long *>(e->d_work) + 1, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemset(reinterpret_cast<unsigned long long *>(e->d_work) + 1, 0, 10 * sizeof(unsigned long long));
     return B200SP_OK;
 }
 

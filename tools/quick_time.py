@@ -27,7 +27,7 @@ def run(name, data, level=3, steps=5):
     ns = int(counts.sum().item())
     if os.environ.get("B200SP_ROLE_PROFILE"):
         import ctypes
-        buf = (ctypes.c_ulonglong * 8)()
+        buf = (ctypes.c_ulonglong * 10)()
         pkg.lib.b200sp_debug_role_cycles(eng._h, buf)
         r = list(buf); st = max(r[7], 1)
         print(f"   per-stage cycles: EH-sum {r[0]/st:9.0f} (per warp {r[0]/st/26:7.0f})  TL {r[1]/st:7.0f}  TS {r[2]/st:7.0f}  P1a {r[3]/st:7.0f}  P1b {r[4]/st:7.0f}  P2 {r[5]/st:7.0f}  wall {r[6]/st:7.0f}")
