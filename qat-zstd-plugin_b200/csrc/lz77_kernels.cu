@@ -156,15 +156,14 @@ struct Shared {         // 32-bit shared-window addresses
     uint32_t tabS;      // u16[1 << kShortBits]
     uint32_t ringH;     // u32[2][kWindow]      H -> T: per table {hash:14 | linked:1 | last:1}, long in the low half
     uint32_t ringC;     // u32[kRingC][kWindow] candidates {long u16 | short u16} (H, T) -> packed prefix maxima (E)
-    uint32_t ringL;     // u32[kRingL][kWindow] P1 -> P2: memoised decisions {end:9 | take lane:5 | offset:17} / hops
+    uint32_t ringL;     // u32[2][kWindow]      P1 -> P2: memoised decisions {end:9 | take lane:5 | offset:17}
     uint32_t gmax;      // u32[kRingC][kGroups] packed farthest-reaching match of each group
     uint32_t gown;      // u32[kRingC][kGroups] lanes whose own prefix maximum is a usable match
-    uint32_t hasA;      // u32[kRingL][32]      P1 -> P2: usable-match mask incl. the carry
-    uint32_t entA;      // u32[kRingL][32]      P1 -> P2: position at which the parse enters each group
+    uint32_t hasA;      // u32[2][kGroups]      P1 -> P2: usable-match mask incl. the carry
+    uint32_t entA;      // u32[2][kGroups]      P1 -> P2: position at which the parse enters each group
     uint32_t mbar;      // u64[kTmaChunks]
     uint32_t work;      // next block index
-    uint32_t curVal;    // P1 -> P1: cursor after the last finished window ...
-    uint32_t curTag;    // ... and which window that was (0xFFFFFFFF = none yet)
+    uint32_t task;      // u32[2] per-stage task counters of the hash/extend warps (double-buffered)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -213,7 +212,7 @@ __device__ __forceinline__ void stage_hash(const Shared &S, uint32_t w, const ui
         const uint32_t vL = valid[i] ? hL[i] : 0u, vS = valid[i] ? hS[i] : 0u;
         const uint32_t ri = ring_byte(group[i], lane);
         sts32(S.ringH + (w & 1u) * (kWindow * 4u) + ri, (vL | (linkedL << 14) | (lastL << 15)) | ((vS | (linkedS << 14) | (lastS << 15)) << 16));
-        sts32(S.ringC + (w % kRingC) * (kWindow * 4u) + ri, cL | (cS << 16));
+        sts32(S.ringC + (w & (kRingC - 1)) * (kWindow * 4u) + ri, cL | (cS << 16));
     }
 }
 
@@ -224,14 +223,13 @@ __device__ __forceinline__ void stage_hash(const Shared &S, uint32_t w, const ui
 __device__ __forceinline__ void stage_table(const Shared &S, uint32_t tab, uint32_t half, uint32_t w, uint32_t lane)
 {
     const uint32_t rh = S.ringH + (w & 1u) * (kWindow * 4u);
-    const uint32_t rc = S.ringC + (w % kRingC) * (kWindow * 4u) + half * 2u;
+    const uint32_t rc = S.ringC + (w & (kRingC - 1)) * (kWindow * 4u) + half * 2u;
     const uint32_t windowBase = w * kWindow, sh = half * 16u;
 #pragma unroll 1
     for (uint32_t g0 = 0; g0 < kGroups; g0 += 8) {
         uint32_t hw[8], tv[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++)      // groups past the window's end: linked, not last -> no table access below
-            hw[k] = g0 + k < kGroups ? (lds32(rh + ring_byte(g0 + k, lane)) >> sh) & 0xFFFFu : 0x4000u;
+        for (int k = 0; k < 8; k++) hw[k] = (lds32(rh + ring_byte(g0 + k, lane)) >> sh) & 0xFFFFu;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const uint32_t ha = tab + (hw[k] & 0x3FFFu) * 2u;
@@ -267,7 +265,7 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32
                                              uint32_t extCap, uint32_t hashWindow = 0, uint32_t hashNh = 0,
                                              uint32_t shortMask = 0)
 {
-    const uint32_t slot = w % kRingC;
+    const uint32_t slot = w & (kRingC - 1);
     const uint32_t idx = S.ringC + slot * (kWindow * 4u) + ring_byte(group, lane);
     const uint32_t cw = ldsc32(idx);
     const uint32_t cL = cw & 0xFFFFu, cS = cw >> 16;
@@ -357,7 +355,7 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32
     }
     sts32(idx, pk);                                      // prefix-max within the group
     const uint32_t own = __ballot_sync(0xFFFFFFFFu, (pk >> 23) >= lane + minMatch);
-    if (lane == 31) { sts32(S.gmax + (slot * 32u + group) * 4u, pk); sts32(S.gown + (slot * 32u + group) * 4u, own); }
+    if (lane == 31) { sts32(S.gmax + (slot * kGroups + group) * 4u, pk); sts32(S.gown + (slot * kGroups + group) * 4u, own); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -389,12 +387,12 @@ __device__ __forceinline__ uint32_t eval_step(uint32_t pkRow, uint32_t group, ui
     return L;
 }
 
-__device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint32_t lane,
+__device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint32_t lane, uint32_t &cursor,
                                               uint32_t minMatch, uint32_t lazyDepth)
 {
-    const uint32_t slot = w % kRingC, base = w * kWindow, slot3 = w % kRingL;
+    const uint32_t slot = w & (kRingC - 1), base = w * kWindow;
     const uint32_t pkRow = S.ringC + slot * (kWindow * 4u);
-    const uint32_t linkRow = S.ringL + slot3 * (kWindow * 4u);
+    const uint32_t linkRow = S.ringL + (w & 1u) * (kWindow * 4u);
     // ---- carry: farthest-reaching match of the previous 8 groups (a match is at most extCap = 256
     // bytes long, so nothing older can reach in), re-based to this group; it wins ties (it is older)
     uint32_t c = 0;
@@ -403,16 +401,15 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
         int gg = static_cast<int>(lane) - static_cast<int>(k);
         uint32_t sl = slot;
         bool ok = true;
-        if (gg < 0) { ok = w > 0; gg += kGroups; sl = (w + kRingC - 1) % kRingC; }
-        const uint32_t v = ok ? lds32(S.gmax + (sl * 32u + gg) * 4u) : 0u;
+        if (gg < 0) { ok = w > 0; gg += kGroups; sl = (w - 1) & (kRingC - 1); }
+        const uint32_t v = ok ? lds32(S.gmax + (sl * kGroups + gg) * 4u) : 0u;
         const uint32_t rel = v >> 23;
         if (rel > 32u * k) c = max(c, ((rel - 32u * k) << 23) | ((32u + k) << 17) | (v & 0x1FFFFu));
     }
     const uint32_t cRel = c >> 23;
     uint32_t cover = 0;
     if (cRel >= minMatch) cover = (cRel - minMatch >= 31u) ? 0xFFFFFFFFu : (2u << (cRel - minMatch)) - 1u;
-    const bool act = lane < kGroups;                    // lanes beyond the window's last group stay inert
-    const uint32_t has = act ? lds32(S.gown + (slot * 32u + lane) * 4u) | cover : 0u;
+    const uint32_t has = lds32(S.gown + (slot * kGroups + lane) * 4u) | cover;
     const uint32_t segStart = base + lane * 32u, segEnd = segStart + 32u;
 
     // ---- every lane guesses that the parser enters its group at its first position; the guesses are
@@ -421,15 +418,8 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
     // that is NOT passed over, i.e. the prefix maximum over live lanes.  A walk depends only on where it
     // starts, and every decision is memoised, so a corrected lane re-evaluates nothing it has seen.
     // First guess: the parse arrives through the carried match (the farthest-reaching one usually is the
-    // one the previous groups ended with); any guess converges to the same fixed point.  That includes
-    // lane 0: where the parse enters this window is published by the warp working on the previous window
-    // (it started one stage earlier and may still be running), so lane 0 starts on a guess as well and
-    // takes the published cursor as soon as it is there.
-    bool known = w == 0;
-    uint32_t cursor = 0;
-    if (!known && lds32(S.curTag) == w - 1u) { __threadfence_block(); cursor = lds32(S.curVal); known = true; }
-    uint32_t entry = (lane == 0 && known) ? max(cursor, base) : segStart + min(cRel, 32u);
-    if (!act) entry = 0xFFFFFFFFu;                      // never live, never changes
+    // one the previous groups ended with); any guess converges to the same fixed point.
+    uint32_t entry = lane == 0 ? max(cursor, base) : segStart + min(cRel, 32u);
     uint32_t visited = 0, pm = 0, walked = 0xFFFFFFFFu, exitPos = 0;
     for (;;) {
         if (entry != walked) {                   // a lane whose entry did not change keeps its exit
@@ -459,34 +449,14 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
             if (lane >= static_cast<uint32_t>(d)) pm = max(pm, o);
         }
         const uint32_t prevMax = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
-        uint32_t want = (lane == 0 || !act) ? entry : max(prevMax, segStart);
-        bool changed = want != entry;
-        if (!__any_sync(0xFFFFFFFFu, changed)) {
-            if (known) break;
-            // converged on a guessed window entry: wait for the real one (warp-uniform spin)
-            while (lds32(S.curTag) != w - 1u) __nanosleep(B200SP_SPIN_NS);
-            __threadfence_block();
-            cursor = lds32(S.curVal);
-            known = true;
-            if (lane == 0) { want = max(cursor, base); changed = want != entry; }
-            if (!__any_sync(0xFFFFFFFFu, changed)) break;
-        } else if (!known && lds32(S.curTag) == w - 1u) {       // warp-uniform: every lane reads the same word
-            __threadfence_block();
-            cursor = lds32(S.curVal);
-            known = true;
-            if (lane == 0) want = max(cursor, base);
-        }
+        const uint32_t want = lane == 0 ? entry : max(prevMax, segStart);
+        const bool changed = want != entry;
         entry = want;
+        if (!__any_sync(0xFFFFFFFFu, changed)) break;
     }
-    sts32(S.hasA + (slot3 * 32u + lane) * 4u, has);
-    sts32(S.entA + (slot3 * 32u + lane) * 4u, entry);
-    // publish where the parse enters the next window (read by the other P1 warp, possibly in this same stage)
-    const uint32_t next = max(__shfl_sync(0xFFFFFFFFu, pm, 31), base + kWindow);
-    if (lane == 0) {
-        sts32(S.curVal, next);
-        __threadfence_block();
-        sts32(S.curTag, w);
-    }
+    cursor = max(__shfl_sync(0xFFFFFFFFu, pm, 31), base + kWindow);
+    sts32(S.hasA + ((w & 1u) * kGroups + lane) * 4u, has);
+    sts32(S.entA + ((w & 1u) * kGroups + lane) * 4u, entry);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -501,10 +471,9 @@ struct EmitCarry {           // uniform across the warp, carried from window to 
 __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t lane, EmitCarry &ec, uint4 *out)
 {
     const uint32_t base = w * kWindow;
-    const uint32_t slot3 = w % kRingL;
-    const uint32_t linkRow = S.ringL + slot3 * (kWindow * 4u);
-    const uint32_t has = lds32(S.hasA + (slot3 * 32u + lane) * 4u);
-    const uint32_t entry = lds32(S.entA + (slot3 * 32u + lane) * 4u);
+    const uint32_t linkRow = S.ringL + (w & 1u) * (kWindow * 4u);
+    const uint32_t has = lds32(S.hasA + ((w & 1u) * kGroups + lane) * 4u);
+    const uint32_t entry = lds32(S.entA + ((w & 1u) * kGroups + lane) * 4u);
     const uint32_t segStart = base + lane * 32u, segEnd = segStart + 32u;
     const uint32_t cur0 = entry < segEnd ? entry - segStart : 32u;
 
@@ -599,18 +568,17 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         S.ringH = p; p += kSmemRingH;
         S.ringC = p; p += kSmemRingC;
         S.ringL = p; p += kSmemRingL;
-        S.gmax = p;  p += kRingC * 32 * 4;
-        S.gown = p;  p += kRingC * 32 * 4;
-        S.hasA = p;  p += kRingL * 32 * 4;
-        S.entA = p;  p += kRingL * 32 * 4;
+        S.gmax = p;  p += kRingC * kGroups * 4;
+        S.gown = p;  p += kRingC * kGroups * 4;
+        S.hasA = p;  p += 2 * kGroups * 4;
+        S.entA = p;  p += 2 * kGroups * 4;
         S.mbar = p;  p += kTmaChunks * 8;
         S.work = p;  p += 8;
-        S.curVal = p; p += 4;
-        S.curTag = p;
+        S.task = p;
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    // Role of this warp: 0 = hash/extend pool, 1 = long table, 2 = short table, 3 / 4 = entries of even / odd
-    // windows (P1), 5 = emit (P2).  (Which scheduler the serial warps sit on made no measurable difference.)
+    // Role of this warp: 0 = hash/extend pool, 1 = long table, 2 = short table, 3 = entries (P1), 4 = emit (P2).
+    // (Which scheduler the four serial warps sit on made no measurable difference.)
     const uint32_t role = warp < kEhWarps ? 0u : warp - kEhWarps + 1u;
 
     if (tid == 0) {
@@ -651,84 +619,74 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         }
         if (tid >= 32 && tid < 32 + (n - bulk))
             sts8(S.in + bulk + tid - 32, gsrc[bulk + tid - 32]);
-        if (tid == 2) sts32(S.curTag, 0xFFFFFFFFu);
         for (uint32_t i = tid; i < (kSmemTabL + kSmemTabS) / 16; i += kThreads)    // tabL and tabS are contiguous
             sts128(S.tabL + i * 16u, 0xFFFFFFFFu);
+        if (tid < 2) sts32(S.task + tid * 4u, kEhWarps);
         __syncthreads();
 
         const uint32_t nh = n >= 8 ? n - 7 : 0;
         const uint32_t nW = (n + kWindow - 1) / kWindow;
         uint32_t chunksSeen = 0;
+        uint32_t cursor = 0;                   // P1: first position the parser has not consumed yet
         EmitCarry ec = {0, 0, 0};              // P2
-
-        // Stage barriers alternate between two named barriers.  An entry warp (P1) takes two stage times per
-        // window: it ARRIVES (without waiting) at the barrier of the stage it starts in, keeps working through
-        // the next stage and waits at that one; with a single barrier its second operation could be counted
-        // into a phase that has not completed yet.
 
 #ifdef B200SP_ROLE_PROFILE
         unsigned long long busy = 0, blockStart = clock64();
 #endif
-        for (uint32_t t = 0; t < nW + 5; t++) {
+        for (uint32_t t = 0; t < nW + 4; t++) {
 #ifdef B200SP_ROLE_PROFILE
             const unsigned long long c0 = clock64();
 #endif
-            bool arrived = false;
             if (role == 0u) {
                 // bytes this stage may touch: hashing window t reads < (t+1)*1024 + 11, extending
                 // window t-2 reads < (t-1)*1024 + extCap + 36 + 3
                 const uint32_t need = min(bulk, (t + 1) * kWindow + 16u);
                 const uint32_t wantChunks = (need + kTmaChunk - 1) / kTmaChunk;
                 while (chunksSeen < wantChunks) { mbar_wait(S.mbar + chunksSeen * 8u, (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
-                // One fused task per pool warp and stage: extend group `warp` of window t-2 and, inside its probe
-                // block, hash group `warp` of window t (the MATCH.ANY latency hides behind the candidate loads).
-                const uint32_t wdx = t - 2;
-                if (t >= 2 && wdx < nW) {
-                    // past the last window the fused hash runs with no valid position (harmless ring writes)
-                    stage_extend<true>(S, wdx, warp, lane, wdx * kWindow + warp * 32u + lane, n, nh, P.minMatch, P.extCap,
-                                       t, t < nW ? nh : 0u, P.shortMask);
-                } else if (t < nW) {
-                    const uint32_t gs[1] = {warp};
-                    stage_hash<1>(S, t, gs, lane, nh, P.shortMask);
+                // One task queue per stage.  Task g extends group g of window t-2 and, inside its probe block,
+                // hashes group g of window t (the MATCH.ANY latency hides behind the candidate loads).
+                const uint32_t nE = (t >= 2 && t - 2 < nW) ? kGroups : 0u;
+                // hash-only tasks exist only while there is no extension work yet (the first two stages)
+                const uint32_t nAll = nE ? nE : (t < nW ? kGroups / kHashGroups : 0u);
+                const uint32_t ctr = S.task + (t & 1u) * 4u;
+                // the first task of every pool warp is its own index (the counter starts at kEhWarps); only the
+                // later ones cost an atomic
+                for (uint32_t id = warp; id < nAll; id = pop_task(ctr, lane)) {
+                    if (id < nE) {
+                        const uint32_t wdx = t - 2;
+                        // past the last window the fused hash runs with no valid position (harmless ring writes)
+                        stage_extend<true>(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap,
+                                           t, t < nW ? nh : 0u, P.shortMask);
+                    } else {
+                        uint32_t gs[kHashGroups];
+#pragma unroll
+                        for (uint32_t i = 0; i < kHashGroups; i++) gs[i] = id - nE + i * (kGroups / kHashGroups);
+                        stage_hash<kHashGroups>(S, t, gs, lane, nh, P.shortMask);
+                    }
                 }
             } else if (role == 1u) {
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabL, 0u, t - 1, lane);
             } else if (role == 2u) {
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabS, 1u, t - 1, lane);
-            } else if (role <= 4u) {
-                const uint32_t w = t - 3;
-                if (t >= 3 && w < nW && (w & 1u) == role - 3u) {
-                    if (t & 1u) asm volatile("bar.arrive 2, %0;" ::"n"(kThreads) : "memory");
-                    else        asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
-                    arrived = true;
-                    stage_entries(S, w, lane, P.minMatch, P.lazyDepth);
-                }
+            } else if (role == 3u) {
+                if (lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, kEhWarps);   // next stage's queue (nobody touches it now)
+                if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, lane, cursor, P.minMatch, P.lazyDepth);
             } else {
-                if (t >= 5) stage_emit(S, t - 5, lane, ec, out);
+                if (t >= 4) stage_emit(S, t - 4, lane, ec, out);
             }
 #ifdef B200SP_ROLE_PROFILE
             busy += clock64() - c0;
-            // slowest pool warp of the stage (developer builds): collected in the spare word after curTag
-            if (role == 0u && lane == 0) atomicMax(reinterpret_cast<unsigned int *>(__cvta_shared_to_generic(S.curTag + 4u)), static_cast<unsigned int>(clock64() - c0));
-            if (role == 5u && lane == 0) {      // the pool warps of this stage are still busy: this is last stage's maximum
-                const uint32_t m = lds32(S.curTag + 4u);
-                sts32(S.curTag + 4u, 0u);
-                if (P.roleCycles) atomicAdd(&P.roleCycles[8], static_cast<unsigned long long>(m));
-            }
 #endif
-            if (!arrived) {
-                if (t & 1u) asm volatile("bar.sync 2, %0;" ::"n"(kThreads) : "memory");
-                else        asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
-            }
+            __syncthreads();
         }
 
 #ifdef B200SP_ROLE_PROFILE          // developer builds only (tools/ab_build.sh NAME -DB200SP_ROLE_PROFILE)
         if (P.roleCycles && lane == 0) {
             atomicAdd(&P.roleCycles[role], busy);
-            if (role == 5u) { atomicAdd(&P.roleCycles[6], clock64() - blockStart); atomicAdd(&P.roleCycles[7], (unsigned long long)(nW + 5)); }
+            if (role == 4u) { atomicAdd(&P.roleCycles[5], clock64() - blockStart); atomicAdd(&P.roleCycles[6], (unsigned long long)(nW + 4)); }
         }
 #endif
-        if (role == 5u && lane == 0) {
+        if (role == 4u && lane == 0) {
             out[ec.nOut] = make_uint4(0u, n - ec.anchor, 0u, 0u);   // trailing literals / block delimiter
             P.counts[b] = ec.nOut + 1u;
         }

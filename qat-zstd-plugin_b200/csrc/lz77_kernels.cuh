@@ -13,18 +13,15 @@
 namespace b200sp {
 
 constexpr uint32_t kBlockMax      = 1u << 17;   // ZSTD_BLOCKSIZE_MAX
-#ifndef B200SP_GROUPS
-#define B200SP_GROUPS 26
-#endif
-// A window is one stage's worth of work: kGroups groups of 32 positions, one per pool warp, so that every
-// pool warp runs exactly one fused task (extend group g of window t-2 + hash group g of window t) per stage:
-// no queue, no atomics, and no warp has to run two tasks back to back while the others wait.
-constexpr uint32_t kGroups        = B200SP_GROUPS;
-constexpr uint32_t kWindow        = kGroups * 32;   // positions per pipeline window
-constexpr uint32_t kRingC         = 5;          // candidate/match ring: windows in flight between hash and the end of entries
-constexpr uint32_t kRingL         = 3;          // link ring: two windows in the entry warps (two stage times each) + one in emit
+constexpr uint32_t kWindow        = 1024;       // positions per pipeline window
+constexpr uint32_t kGroups        = kWindow / 32;
+constexpr uint32_t kRingC         = 4;          // candidate/match ring: windows in flight between hash and entries
 constexpr uint32_t kLongBits      = 14;
 constexpr uint32_t kShortBits     = 14;
+#ifndef B200SP_HASH_GROUPS
+#define B200SP_HASH_GROUPS 1
+#endif
+constexpr uint32_t kHashGroups    = B200SP_HASH_GROUPS;   // groups per hash task (their MATCH.ANY latencies overlap)
 constexpr uint32_t kProbe         = 16;         // bytes compared per candidate before a winner is picked
 constexpr uint32_t kMaxExtCap     = 256;
 constexpr uint32_t kInputPad      = 320;        // readable slack after the block in shared memory
@@ -32,14 +29,14 @@ constexpr uint32_t kTmaChunk      = 16384;
 constexpr uint32_t kTmaChunks     = kBlockMax / kTmaChunk;
 
 #ifndef B200SP_EH_WARPS
-#define B200SP_EH_WARPS 26
+#define B200SP_EH_WARPS 28
 #endif
 constexpr int kEhWarps     = B200SP_EH_WARPS;   // hash + extension warps
 constexpr int kWarpTabL    = kEhWarps;          // serial owner of the long-hash table
 constexpr int kWarpTabS    = kEhWarps + 1;      // serial owner of the short-hash table
-constexpr int kWarpEntries = kEhWarps + 2;      // P1 (two warps: even / odd windows, two stage times per window)
-constexpr int kWarpEmit    = kEhWarps + 4;      // P2: scans + ZSTD_Sequence stores
-constexpr int kNumWarps    = kEhWarps + 5;
+constexpr int kWarpEntries = kEhWarps + 2;      // P1: lazy decisions + group entries (speculative, lane-parallel)
+constexpr int kWarpEmit    = kEhWarps + 3;      // P2: scans + ZSTD_Sequence stores
+constexpr int kNumWarps    = kEhWarps + 4;
 constexpr int kThreads     = kNumWarps * 32;
 
 // Shared-memory carve-up (bytes)
@@ -48,12 +45,10 @@ constexpr uint32_t kSmemTabL    = (1u << kLongBits) * 2;
 constexpr uint32_t kSmemTabS    = (1u << kShortBits) * 2;
 constexpr uint32_t kSmemRingH   = 2 * kWindow * 4;        // hash words, H -> T
 constexpr uint32_t kSmemRingC   = kRingC * kWindow * 4;   // candidates -> packed prefix maxima, H/T -> E -> P1
-constexpr uint32_t kSmemRingL   = kRingL * kWindow * 4;   // memoised parse decisions, P1 -> P2
-constexpr uint32_t kSmemGroup   = (2 * kRingC + 2 * kRingL) * 32 * 4;   // gmax, gown, hasA, entA (32 entries per window)
-constexpr uint32_t kSmemMisc    = 128;          // mbarriers, work-item slot, cursor hand-off between the entry warps
+constexpr uint32_t kSmemRingL   = 2 * kWindow * 4;        // memoised parse decisions, P1 -> P2
+constexpr uint32_t kSmemGroup   = (2 * kRingC + 4) * kGroups * 4;   // gmax, gown, hasA, entA
+constexpr uint32_t kSmemMisc    = 128;          // mbarriers + work-item slot + task counters
 constexpr uint32_t kSmemTotal   = kSmemInput + kSmemTabL + kSmemTabS + kSmemRingH + kSmemRingC + kSmemRingL + kSmemGroup + kSmemMisc;
-static_assert(kGroups == static_cast<uint32_t>(kEhWarps), "one fused task per pool warp and stage");
-static_assert(kGroups >= 9 && kGroups <= 32, "a lane of the parse warps owns one group; carries look 8 groups back");
 static_assert(kSmemTotal <= 232448, "exceeds 227 KB of shared memory per CTA");
 
 struct ParseParams {
