@@ -181,3 +181,51 @@ def test_generate_sequences_hand_off(pkg, oracle):
     finally:
         q.freeSeqProdState(st)
         q.stopQatDevice()
+
+
+def test_many_threads_each_with_its_own_state(pkg, oracle):
+    """The reference is used from many threads, one CCtx + one producer state per thread
+    (/root/reference/test/benchmark.c:222-402, README "multi-thread"); start/stop are process-wide and
+    idempotent (/root/reference/src/qatseqprod.c:948-964).  Four threads compress different buffers at
+    once through the registered producer: every frame round-trips, no producer error, same sizes as
+    the single-threaded run."""
+    import threading
+    q = pkg.QatSeqProd
+    bufs = [datagen.mixed_corpus(4 * BLOCK + 1000 * (i + 1), seed=50 + i) for i in range(4)]
+    ref = []
+    assert q.startQatDevice() == pkg.QZSTD_OK
+    st0 = q.createSeqProdState()
+    for b in bufs:
+        ref.append(oracle.compress_with_producer(b, q.producer, st0, chunk=BLOCK, level=3)["csize"])
+    q.freeSeqProdState(st0)
+    out = [None] * 4
+
+    def work(i):
+        assert q.startQatDevice() == pkg.QZSTD_OK            # idempotent, from any thread
+        st = q.createSeqProdState()
+        try:
+            for _ in range(3):
+                out[i] = oracle.compress_with_producer(bufs[i], q.producer, st, chunk=BLOCK, level=3)
+        finally:
+            q.freeSeqProdState(st)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts: t.start()
+    for t in ts: t.join()
+    q.stopQatDevice()
+    for i in range(4):
+        assert out[i] is not None and out[i]["round_trip"] and out[i]["errors"] == 0
+        assert out[i]["csize"] == ref[i]
+
+
+def test_benchmark_tool_four_threads(pkg, tmp_path):
+    """tools/qzstd_benchmark (the mirror of the reference's test/benchmark.c) with -t4, plugin mode."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tools", "qzstd_benchmark")
+    f = tmp_path / "in.bin"
+    f.write_bytes(datagen.mixed_corpus(6 * BLOCK + 777, seed=61))
+    r = subprocess.run([exe, "-t4", "-l2", "-c128K", "-E1", "-L3", "-m1", str(f)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "software fallbacks: 0" in r.stderr and r.stderr.strip().endswith("PASS"), r.stderr
+    assert r.stderr.count("PASS") >= 5
