@@ -54,6 +54,12 @@ int b200sp_driver_device_count(void);
 /* Number of usable (sm_100, enough shared memory) devices; 0 if none; <0 on driver failure. */
 int b200sp_device_count(void);
 
+/* Pays the one-time costs of a device up front (CUDA context, module load, opt-in shared memory), so that
+ * the first parsed block does not: the counterpart of the instance start-up the reference does inside
+ * QZSTD_startQatDevice (cpaDcStartInstance etc., /root/reference/src/qatseqprod.c:824-903).  Optional and
+ * idempotent; engines work without it. */
+int b200sp_warmup(int device);
+
 /* Engine = one device + one stream + scratch buffers.  Not thread-safe: one engine per caller
  * thread, like one QZSTD state per CCtx (/root/reference/src/qatseqprod.h:139-151). */
 int  b200sp_engine_create(int device, b200sp_engine **engine);

@@ -208,6 +208,19 @@ int b200sp_device_count(void)
     return usable;
 }
 
+int b200sp_warmup(int device)
+{
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n == 0) { (void)cudaGetLastError(); return fail(B200SP_ENODEVICE, "no CUDA device", ce); }
+    if (device < 0 || device >= n) return fail(B200SP_EINVAL, "warmup: device index out of range");
+    if (!device_usable(device)) return fail(B200SP_EUNSUPPORTED, "device is not sm_100 with 227 KB shared memory per CTA");
+    CU_TRY(cudaSetDevice(device), "cudaSetDevice");
+    CU_TRY(cudaFree(nullptr), "context creation");
+    CU_TRY(b200sp::configure_kernels(), "cudaFuncSetAttribute(max dynamic smem)");      // loads the module
+    return B200SP_OK;
+}
+
 int b200sp_engine_create(int device, b200sp_engine **out)
 {
     if (!out) return fail(B200SP_EINVAL, "engine_create: null out pointer");

@@ -84,6 +84,11 @@ int QZSTD_startQatDevice(void)
     if (QZSTD_STARTED == g_process.status) {
         /* a device with the required capability?  (instance discovery + capability filter, :529-663) */
         g_process.status = b200sp_device_count() > 0 ? QZSTD_OK : QZSTD_STARTED;
+        /* context + module load now, not inside the first block (the reference starts its instances here too) */
+        if (QZSTD_OK == g_process.status && b200sp_warmup(0) != B200SP_OK) {
+            QZSTD_LOG(1, "Device warm-up failed: %s\n", b200sp_error_string());
+            g_process.status = QZSTD_STARTED;
+        }
     }
     status = g_process.status;
     QZSTD_LOG(2, "InitStatus: %d\n", status);
