@@ -136,18 +136,11 @@ __device__ __forceinline__ uint32_t pop_task(uint32_t ctrAddr, uint32_t lane)
     return __shfl_sync(0xFFFFFFFFu, id, 0);
 }
 
-__device__ __forceinline__ uint32_t ring_index(uint32_t group, uint32_t lane)
-{
-    return group * 32u + (lane ^ group);   // XOR swizzle: conflict-free by group and by lane
-}
+// XOR swizzle of the ring words: conflict-free by group (a warp writes its group) and by lane (a parse lane
+// reads the same local position in 32 groups).
 __device__ __forceinline__ uint32_t ring_byte(uint32_t group, uint32_t lane)   // byte offset of a 32-bit ring word
 {
     return (group * 32u + (lane ^ group)) * 4u;
-}
-
-__device__ __forceinline__ int32_t gain_of(uint32_t len, uint32_t off)
-{
-    return static_cast<int32_t>(len * 4u) - static_cast<int32_t>(31 - __clz(off + 1u));
 }
 
 struct Shared {         // 32-bit shared-window addresses
