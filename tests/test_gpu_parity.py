@@ -229,3 +229,22 @@ def test_benchmark_tool_four_threads(pkg, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "software fallbacks: 0" in r.stderr and r.stderr.strip().endswith("PASS"), r.stderr
     assert r.stderr.count("PASS") >= 5
+
+
+def test_parse_host_many_blocks_and_pageable_input(pkg, oracle, engine):
+    """The pipelined host path (b200sp_parse_host) with more blocks than the chunk plan has one-wave slots
+    for (6 100 blocks of 4 KiB: chunks grow beyond one wave), a block size whose stride is padded (5 000 B ->
+    2-D copies), pageable input (staging memcpy), and a ragged tail.  Every block equals the serial model."""
+    data = datagen.mixed_corpus(6100 * 4096 - 1234, seed=71)
+    for bs in (4096, 5000):
+        part = data if bs == 4096 else data[:400 * 5000 + 77]
+        counts, offsets, seqs = engine.parse_host_numpy(part, block_size=bs, level=3)
+        nb = (len(part) + bs - 1) // bs
+        assert counts.shape[0] == nb and int(offsets[nb]) == seqs.shape[0] == int(counts.sum())
+        step = 1 if bs == 5000 else 37                      # every block of the small case, a sample of the big one
+        for b in list(range(0, nb, step)) + [nb - 1]:
+            got = seqs[int(offsets[b]):int(offsets[b]) + int(counts[b])]
+            want = oracle.model_block(part[b * bs:(b + 1) * bs], 3)
+            assert got.shape == want.shape and (got == want).all(), f"block {b} of {nb} (block size {bs})"
+        total = sum(int(seqs[int(offsets[b]):int(offsets[b + 1]), 1:3].sum()) for b in (0, nb // 2, nb - 1))
+        assert total == sum(len(part[b * bs:(b + 1) * bs]) for b in (0, nb // 2, nb - 1))
