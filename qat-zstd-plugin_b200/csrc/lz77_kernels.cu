@@ -140,7 +140,7 @@ __device__ __forceinline__ uint32_t pop_task(uint32_t ctrAddr, uint32_t lane)
 // reads the same local position in 32 groups).
 __device__ __forceinline__ uint32_t ring_byte(uint32_t group, uint32_t lane)   // byte offset of a 32-bit ring word
 {
-    return (group * 32u + (lane ^ group)) * 4u;
+    return (group * 32u + (lane ^ (group & 31u))) * 4u;
 }
 
 struct Shared {         // 32-bit shared-window addresses
@@ -222,7 +222,8 @@ __device__ __forceinline__ void stage_table(const Shared &S, uint32_t tab, uint3
     for (uint32_t g0 = 0; g0 < kGroups; g0 += 8) {
         uint32_t hw[8], tv[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) hw[k] = (lds32(rh + ring_byte(g0 + k, lane)) >> sh) & 0xFFFFu;
+        for (int k = 0; k < 8; k++)      // groups past the window's end: linked, not last -> no table access below
+            hw[k] = g0 + k < kGroups ? (lds32(rh + ring_byte(g0 + k, lane)) >> sh) & 0xFFFFu : 0x4000u;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const uint32_t ha = tab + (hw[k] & 0x3FFFu) * 2u;
@@ -348,7 +349,7 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32
     }
     sts32(idx, pk);                                      // prefix-max within the group
     const uint32_t own = __ballot_sync(0xFFFFFFFFu, (pk >> 23) >= lane + minMatch);
-    if (lane == 31) { sts32(S.gmax + (slot * kGroups + group) * 4u, pk); sts32(S.gown + (slot * kGroups + group) * 4u, own); }
+    if (lane == 31) { sts32(S.gmax + (slot * 64u + group) * 4u, pk); sts32(S.gown + (slot * 64u + group) * 4u, own); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -380,10 +381,12 @@ __device__ __forceinline__ uint32_t eval_step(uint32_t pkRow, uint32_t group, ui
     return L;
 }
 
-__device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint32_t lane, uint32_t &cursor,
+__device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint32_t half, uint32_t lane, uint32_t &cursor,
                                               uint32_t minMatch, uint32_t lazyDepth)
 {
-    const uint32_t slot = w & (kRingC - 1), base = w * kWindow;
+    // lane j owns group half * kHalf + j of the window; `cursor` chains the halves and the windows
+    const uint32_t slot = w & (kRingC - 1), base = w * kWindow, group = half * kHalf + lane;
+    const bool act = lane < kHalf;
     const uint32_t pkRow = S.ringC + slot * (kWindow * 4u);
     const uint32_t linkRow = S.ringL + (w & 1u) * (kWindow * 4u);
     // ---- carry: farthest-reaching match of the previous 8 groups (a match is at most extCap = 256
@@ -391,19 +394,19 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
     uint32_t c = 0;
 #pragma unroll
     for (uint32_t k = 1; k <= 8; k++) {
-        int gg = static_cast<int>(lane) - static_cast<int>(k);
+        int gg = static_cast<int>(group) - static_cast<int>(k);
         uint32_t sl = slot;
         bool ok = true;
         if (gg < 0) { ok = w > 0; gg += kGroups; sl = (w - 1) & (kRingC - 1); }
-        const uint32_t v = ok ? lds32(S.gmax + (sl * kGroups + gg) * 4u) : 0u;
+        const uint32_t v = ok ? lds32(S.gmax + (sl * 64u + gg) * 4u) : 0u;
         const uint32_t rel = v >> 23;
         if (rel > 32u * k) c = max(c, ((rel - 32u * k) << 23) | ((32u + k) << 17) | (v & 0x1FFFFu));
     }
     const uint32_t cRel = c >> 23;
     uint32_t cover = 0;
     if (cRel >= minMatch) cover = (cRel - minMatch >= 31u) ? 0xFFFFFFFFu : (2u << (cRel - minMatch)) - 1u;
-    const uint32_t has = lds32(S.gown + (slot * kGroups + lane) * 4u) | cover;
-    const uint32_t segStart = base + lane * 32u, segEnd = segStart + 32u;
+    const uint32_t has = act ? lds32(S.gown + (slot * 64u + group) * 4u) | cover : 0u;
+    const uint32_t segStart = base + group * 32u, segEnd = segStart + 32u;
 
     // ---- every lane guesses that the parser enters its group at its first position; the guesses are
     // corrected from lane 0 upward until nothing changes.  A lane whose entry lies beyond its group is
@@ -412,7 +415,8 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
     // starts, and every decision is memoised, so a corrected lane re-evaluates nothing it has seen.
     // First guess: the parse arrives through the carried match (the farthest-reaching one usually is the
     // one the previous groups ended with); any guess converges to the same fixed point.
-    uint32_t entry = lane == 0 ? max(cursor, base) : segStart + min(cRel, 32u);
+    uint32_t entry = lane == 0 ? max(cursor, segStart) : segStart + min(cRel, 32u);
+    if (!act) entry = 0xFFFFFFFFu;                      // lanes beyond the half stay inert: never live, never change
     uint32_t visited = 0, pm = 0, walked = 0xFFFFFFFFu, exitPos = 0;
     for (;;) {
         if (entry != walked) {                   // a lane whose entry did not change keeps its exit
@@ -424,10 +428,10 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
                 if (!m) { cur = 32u; break; }
                 const uint32_t p0 = __ffs(m) - 1;
                 uint32_t L;
-                if ((visited >> p0) & 1u) L = lds32(linkRow + ring_byte(lane, p0));
+                if ((visited >> p0) & 1u) L = lds32(linkRow + ring_byte(group, p0));
                 else {
-                    L = eval_step(pkRow, lane, p0, c, has, lazyDepth);
-                    sts32(linkRow + ring_byte(lane, p0), L);
+                    L = eval_step(pkRow, group, p0, c, has, lazyDepth);
+                    sts32(linkRow + ring_byte(group, p0), L);
                     visited |= 1u << p0;
                 }
                 cur = (L >> 22) & 0x1FFu;
@@ -442,14 +446,16 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
             if (lane >= static_cast<uint32_t>(d)) pm = max(pm, o);
         }
         const uint32_t prevMax = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
-        const uint32_t want = lane == 0 ? entry : max(prevMax, segStart);
+        const uint32_t want = (lane == 0 || !act) ? entry : max(prevMax, segStart);
         const bool changed = want != entry;
         entry = want;
         if (!__any_sync(0xFFFFFFFFu, changed)) break;
     }
-    cursor = max(__shfl_sync(0xFFFFFFFFu, pm, 31), base + kWindow);
-    sts32(S.hasA + ((w & 1u) * kGroups + lane) * 4u, has);
-    sts32(S.entA + ((w & 1u) * kGroups + lane) * 4u, entry);
+    cursor = max(__shfl_sync(0xFFFFFFFFu, pm, 31), base + (half + 1u) * (kHalf * 32u));
+    if (act) {
+        sts32(S.hasA + ((w & 1u) * 64u + group) * 4u, has);
+        sts32(S.entA + ((w & 1u) * 64u + group) * 4u, entry);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -461,13 +467,14 @@ struct EmitCarry {           // uniform across the warp, carried from window to 
     uint32_t nOut;           // sequences written so far
 };
 
-__device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t lane, EmitCarry &ec, uint4 *out)
+__device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t half, uint32_t lane, EmitCarry &ec, uint4 *out)
 {
-    const uint32_t base = w * kWindow;
+    const uint32_t base = w * kWindow, group = half * kHalf + lane;
+    const bool act = lane < kHalf;
     const uint32_t linkRow = S.ringL + (w & 1u) * (kWindow * 4u);
-    const uint32_t has = lds32(S.hasA + ((w & 1u) * kGroups + lane) * 4u);
-    const uint32_t entry = lds32(S.entA + ((w & 1u) * kGroups + lane) * 4u);
-    const uint32_t segStart = base + lane * 32u, segEnd = segStart + 32u;
+    const uint32_t has = act ? lds32(S.hasA + ((w & 1u) * 64u + group) * 4u) : 0u;
+    const uint32_t entry = act ? lds32(S.entA + ((w & 1u) * 64u + group) * 4u) : 0xFFFFFFFFu;
+    const uint32_t segStart = base + group * 32u, segEnd = segStart + 32u;
     const uint32_t cur0 = entry < segEnd ? entry - segStart : 32u;
 
     // ---- counting walk along the memoised links
@@ -477,7 +484,7 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
         while (cur < 32u) {
             const uint32_t m = has & (0xFFFFFFFFu << cur);
             if (!m) break;
-            const uint32_t L = lds32(linkRow + ring_byte(lane, __ffs(m) - 1));
+            const uint32_t L = lds32(linkRow + ring_byte(group, __ffs(m) - 1));
             if (L >> 31) { cur = (L >> 22) & 0x1FFu; continue; }         // hop: a later start is better (lazy)
             const uint32_t p = segStart + ((L >> 17) & 31u), end = segStart + (L >> 22), off = L & 0x1FFFFu;
             if (cnt && p == lastEnd && off == lastOff) merges++;
@@ -522,7 +529,7 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
         while (cur < 32u) {
             const uint32_t m = has & (0xFFFFFFFFu << cur);
             if (!m) break;
-            const uint32_t L = lds32(linkRow + ring_byte(lane, __ffs(m) - 1));
+            const uint32_t L = lds32(linkRow + ring_byte(group, __ffs(m) - 1));
             if (L >> 31) { cur = (L >> 22) & 0x1FFu; continue; }         // hop
             const uint32_t p = segStart + ((L >> 17) & 31u), end = segStart + (L >> 22), o = L & 0x1FFFFu;
             const uint32_t lit = p - anchor, len = end - p;
@@ -561,10 +568,10 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         S.ringH = p; p += kSmemRingH;
         S.ringC = p; p += kSmemRingC;
         S.ringL = p; p += kSmemRingL;
-        S.gmax = p;  p += kRingC * kGroups * 4;
-        S.gown = p;  p += kRingC * kGroups * 4;
-        S.hasA = p;  p += 2 * kGroups * 4;
-        S.entA = p;  p += 2 * kGroups * 4;
+        S.gmax = p;  p += kRingC * 64 * 4;
+        S.gown = p;  p += kRingC * 64 * 4;
+        S.hasA = p;  p += 2 * 64 * 4;
+        S.entA = p;  p += 2 * 64 * 4;
         S.mbar = p;  p += kTmaChunks * 8;
         S.work = p;  p += 8;
         S.task = p;
@@ -663,9 +670,11 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabS, 1u, t - 1, lane);
             } else if (role == 3u) {
                 if (lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, kEhWarps);   // next stage's queue (nobody touches it now)
-                if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, lane, cursor, P.minMatch, P.lazyDepth);
+                if (t >= 3 && t - 3 < nW)
+                    for (uint32_t half = 0; half < 2; half++) stage_entries(S, t - 3, half, lane, cursor, P.minMatch, P.lazyDepth);
             } else {
-                if (t >= 4) stage_emit(S, t - 4, lane, ec, out);
+                if (t >= 4)
+                    for (uint32_t half = 0; half < 2; half++) stage_emit(S, t - 4, half, lane, ec, out);
             }
 #ifdef B200SP_ROLE_PROFILE
             busy += clock64() - c0;

@@ -13,11 +13,19 @@
 namespace b200sp {
 
 constexpr uint32_t kBlockMax      = 1u << 17;   // ZSTD_BLOCKSIZE_MAX
-constexpr uint32_t kWindow        = 1024;       // positions per pipeline window
-constexpr uint32_t kGroups        = kWindow / 32;
+#ifndef B200SP_GROUPS
+#define B200SP_GROUPS 52
+#endif
+// A window is one stage's worth of work: kGroups groups of 32 positions = two tasks per pool warp, so that the
+// task queue balances inside a stage (32 tasks on 28 warps made every stage last two tasks with most warps
+// waiting through the second).  The parse warps own one group per lane: they take a window in two halves.
+constexpr uint32_t kGroups        = B200SP_GROUPS;
+constexpr uint32_t kHalf          = kGroups / 2;    // groups per parse pass (<= 32: one lane each)
+constexpr uint32_t kWindow        = kGroups * 32;   // positions per pipeline window
+static_assert(kGroups % 2 == 0 && kHalf >= 9 && kHalf <= 32 && kGroups <= 64, "two parse passes of at most 32 groups; carries look 8 groups back");
 constexpr uint32_t kRingC         = 4;          // candidate/match ring: windows in flight between hash and entries
 constexpr uint32_t kLongBits      = 14;
-constexpr uint32_t kShortBits     = 14;
+constexpr uint32_t kShortBits     = 12;         // 8 KiB: the shared memory the wider window needs comes from here (+1.1 % in size)
 #ifndef B200SP_HASH_GROUPS
 #define B200SP_HASH_GROUPS 1
 #endif
@@ -46,7 +54,7 @@ constexpr uint32_t kSmemTabS    = (1u << kShortBits) * 2;
 constexpr uint32_t kSmemRingH   = 2 * kWindow * 4;        // hash words, H -> T
 constexpr uint32_t kSmemRingC   = kRingC * kWindow * 4;   // candidates -> packed prefix maxima, H/T -> E -> P1
 constexpr uint32_t kSmemRingL   = 2 * kWindow * 4;        // memoised parse decisions, P1 -> P2
-constexpr uint32_t kSmemGroup   = (2 * kRingC + 4) * kGroups * 4;   // gmax, gown, hasA, entA
+constexpr uint32_t kSmemGroup   = (2 * kRingC + 4) * 64 * 4;   // gmax, gown, hasA, entA (64 entries per window)
 constexpr uint32_t kSmemMisc    = 128;          // mbarriers + work-item slot + task counters
 constexpr uint32_t kSmemTotal   = kSmemInput + kSmemTabL + kSmemTabS + kSmemRingH + kSmemRingC + kSmemRingL + kSmemGroup + kSmemMisc;
 static_assert(kSmemTotal <= 232448, "exceeds 227 KB of shared memory per CTA");
