@@ -157,6 +157,11 @@ struct Shared {         // 32-bit shared-window addresses
     uint32_t mbar;      // u64[kTmaChunks]
     uint32_t work;      // next block index
     uint32_t task;      // u32[2] per-stage task counters of the hash/extend warps (double-buffered)
+    uint32_t curVal;    // entry warps: where the parse enters the next half window ...
+    uint32_t curTag;    // ... and which half that is: 2 * window + half + 1 of the publisher (0 = none yet)
+    uint32_t ecVal;     // emit warps: u32[3] anchor, previous offset, sequences written, after the publisher's half ...
+    uint32_t ecTag;     // ... same numbering
+    uint32_t emTag;     // emit warps: window + 1 once the first half's sequences are in memory
 };
 
 // ------------------------------------------------------------------------------------------
@@ -381,10 +386,13 @@ __device__ __forceinline__ uint32_t eval_step(uint32_t pkRow, uint32_t group, ui
     return L;
 }
 
-__device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint32_t half, uint32_t lane, uint32_t &cursor,
+__device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint32_t half, uint32_t lane,
                                               uint32_t minMatch, uint32_t lazyDepth)
 {
-    // lane j owns group half * kHalf + j of the window; `cursor` chains the halves and the windows
+    // Lane j owns group half * kHalf + j of the window.  The two halves of a window are handled by two warps in
+    // the same stage: where the parse enters a half is published by the warp of the half before it (the second
+    // half of the previous window: last stage; the first half of this window: any moment now), tagged
+    // 2 * window + half + 1.
     const uint32_t slot = w & (kRingC - 1), base = w * kWindow, group = half * kHalf + lane;
     const bool act = lane < kHalf;
     const uint32_t pkRow = S.ringC + slot * (kWindow * 4u);
@@ -415,7 +423,12 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
     // starts, and every decision is memoised, so a corrected lane re-evaluates nothing it has seen.
     // First guess: the parse arrives through the carried match (the farthest-reaching one usually is the
     // one the previous groups ended with); any guess converges to the same fixed point.
-    uint32_t entry = lane == 0 ? max(cursor, segStart) : segStart + min(cRel, 32u);
+    // That includes lane 0: it starts on a guess as well and takes the published cursor as soon as it is there.
+    const uint32_t expect = 2u * w + half;              // tag of the half before this one
+    bool known = expect == 0u;
+    uint32_t cursor = 0;
+    if (!known && lds32(S.curTag) == expect) { __threadfence_block(); cursor = lds32(S.curVal); known = true; }
+    uint32_t entry = (lane == 0 && known) ? max(cursor, segStart) : segStart + min(cRel, 32u);
     if (!act) entry = 0xFFFFFFFFu;                      // lanes beyond the half stay inert: never live, never change
     uint32_t visited = 0, pm = 0, walked = 0xFFFFFFFFu, exitPos = 0;
     for (;;) {
@@ -446,15 +459,35 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
             if (lane >= static_cast<uint32_t>(d)) pm = max(pm, o);
         }
         const uint32_t prevMax = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
-        const uint32_t want = (lane == 0 || !act) ? entry : max(prevMax, segStart);
-        const bool changed = want != entry;
+        uint32_t want = (lane == 0 || !act) ? entry : max(prevMax, segStart);
+        bool changed = want != entry;
+        if (!__any_sync(0xFFFFFFFFu, changed)) {
+            if (known) break;
+            // converged on a guessed entry of the half: wait for the real one (warp-uniform spin)
+            while (lds32(S.curTag) != expect) __nanosleep(B200SP_SPIN_NS);
+            __threadfence_block();
+            cursor = lds32(S.curVal);
+            known = true;
+            if (lane == 0) { want = max(cursor, segStart); changed = want != entry; }
+            if (!__any_sync(0xFFFFFFFFu, changed)) break;
+        } else if (!known && lds32(S.curTag) == expect) {       // warp-uniform: every lane reads the same word
+            __threadfence_block();
+            cursor = lds32(S.curVal);
+            known = true;
+            if (lane == 0) want = max(cursor, segStart);
+        }
         entry = want;
-        if (!__any_sync(0xFFFFFFFFu, changed)) break;
     }
-    cursor = max(__shfl_sync(0xFFFFFFFFu, pm, 31), base + (half + 1u) * (kHalf * 32u));
     if (act) {
         sts32(S.hasA + ((w & 1u) * 64u + group) * 4u, has);
         sts32(S.entA + ((w & 1u) * 64u + group) * 4u, entry);
+    }
+    // publish where the parse enters the next half
+    const uint32_t next = max(__shfl_sync(0xFFFFFFFFu, pm, 31), base + (half + 1u) * (kHalf * 32u));
+    if (lane == 0) {
+        sts32(S.curVal, next);
+        __threadfence_block();
+        sts32(S.curTag, expect + 1u);
     }
 }
 
@@ -467,6 +500,9 @@ struct EmitCarry {           // uniform across the warp, carried from window to 
     uint32_t nOut;           // sequences written so far
 };
 
+// The two halves of a window are emitted by two warps in the same stage.  The carry (anchor, previous offset,
+// sequences written) travels through shared memory like the entry cursor: the first half's warp publishes it
+// right after its scans, so the second half's warp - which has done its counting walk meanwhile - waits little.
 __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t half, uint32_t lane, EmitCarry &ec, uint4 *out)
 {
     const uint32_t base = w * kWindow, group = half * kHalf + lane;
@@ -495,6 +531,17 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
     }
     __syncwarp();
 
+    // ---- the carry of the half before this one
+    {
+        const uint32_t expect = 2u * w + half;
+        if (expect == 0u) { ec.anchor = 0u; ec.prevOff = 0u; ec.nOut = 0u; }
+        else {
+            while (lds32(S.ecTag) != expect) __nanosleep(B200SP_SPIN_NS);
+            __threadfence_block();
+            ec.anchor = lds32(S.ecVal); ec.prevOff = lds32(S.ecVal + 4u); ec.nOut = lds32(S.ecVal + 8u);
+        }
+    }
+
     // ---- anchor / previous offset at each lane's entry: exclusive "last match" scan
     uint32_t aE = cnt ? lastEnd : 0u, aO = lastOff;
 #pragma unroll
@@ -518,6 +565,13 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
     }
     const uint32_t firstIdx = ec.nOut + incl - fresh;
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (totE) { ec.anchor = totE; ec.prevOff = totO; }
+    ec.nOut += total;
+    if (lane == 0) {            // the next half can run its scans while this one emits
+        sts32(S.ecVal, ec.anchor); sts32(S.ecVal + 4u, ec.prevOff); sts32(S.ecVal + 8u, ec.nOut);
+        __threadfence_block();
+        sts32(S.ecTag, 2u * w + half + 1u);
+    }
 
     // ---- emitting walk.  New sequences go to out[firstIdx...]; a leading continuation of an earlier
     // lane's sequence is added to out[firstIdx - 1].matchLength afterwards.
@@ -545,11 +599,18 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
         if (haveOpen) out[outIdx] = make_uint4(openOff, openLit, openLen, 0u);
     }
     __syncwarp();
+    // A continuation is added to a sequence an earlier lane wrote - for the second half possibly a lane of the
+    // first half's warp, which must have stored it before (its stores of earlier windows are a stage old).
+    if (half == 1u) {
+        while (lds32(S.emTag) != w + 1u) __nanosleep(B200SP_SPIN_NS);
+        __threadfence();
+    }
     if (headAdd) atomicAdd(&out[firstIdx - 1].z, headAdd);   // continuation of an earlier lane's sequence
     __syncwarp();
-
-    if (totE) { ec.anchor = totE; ec.prevOff = totO; }
-    ec.nOut += total;
+    if (half == 0u && lane == 0) {
+        __threadfence();
+        sts32(S.emTag, w + 1u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -574,11 +635,16 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         S.entA = p;  p += 2 * 64 * 4;
         S.mbar = p;  p += kTmaChunks * 8;
         S.work = p;  p += 8;
-        S.task = p;
+        S.task = p;  p += 8;
+        S.curVal = p; p += 4;
+        S.curTag = p; p += 4;
+        S.ecVal = p;  p += 12;
+        S.ecTag = p;  p += 4;
+        S.emTag = p;
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    // Role of this warp: 0 = hash/extend pool, 1 = long table, 2 = short table, 3 = entries (P1), 4 = emit (P2).
-    // (Which scheduler the four serial warps sit on made no measurable difference.)
+    // Role of this warp: 0 = hash/extend pool, 1 = long table, 2 = short table, 3 / 4 = entries of the first /
+    // second half window (P1), 5 / 6 = emit of the first / second half window (P2).
     const uint32_t role = warp < kEhWarps ? 0u : warp - kEhWarps + 1u;
 
     if (tid == 0) {
@@ -622,13 +688,13 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         for (uint32_t i = tid; i < (kSmemTabL + kSmemTabS) / 16; i += kThreads)    // tabL and tabS are contiguous
             sts128(S.tabL + i * 16u, 0xFFFFFFFFu);
         if (tid < 2) sts32(S.task + tid * 4u, kEhWarps);
+        if (tid == 2) { sts32(S.curTag, 0u); sts32(S.ecTag, 0u); sts32(S.emTag, 0u); }
         __syncthreads();
 
         const uint32_t nh = n >= 8 ? n - 7 : 0;
         const uint32_t nW = (n + kWindow - 1) / kWindow;
         uint32_t chunksSeen = 0;
-        uint32_t cursor = 0;                   // P1: first position the parser has not consumed yet
-        EmitCarry ec = {0, 0, 0};              // P2
+        EmitCarry ec = {0, 0, 0};              // P2 (loaded from / published to shared memory every half window)
 
 #ifdef B200SP_ROLE_PROFILE
         unsigned long long busy = 0, blockStart = clock64();
@@ -668,13 +734,11 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabL, 0u, t - 1, lane);
             } else if (role == 2u) {
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabS, 1u, t - 1, lane);
-            } else if (role == 3u) {
-                if (lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, kEhWarps);   // next stage's queue (nobody touches it now)
-                if (t >= 3 && t - 3 < nW)
-                    for (uint32_t half = 0; half < 2; half++) stage_entries(S, t - 3, half, lane, cursor, P.minMatch, P.lazyDepth);
+            } else if (role <= 4u) {
+                if (role == 3u && lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, kEhWarps);   // next stage's queue (nobody touches it now)
+                if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, role - 3u, lane, P.minMatch, P.lazyDepth);
             } else {
-                if (t >= 4)
-                    for (uint32_t half = 0; half < 2; half++) stage_emit(S, t - 4, half, lane, ec, out);
+                if (t >= 4) stage_emit(S, t - 4, role - 5u, lane, ec, out);
             }
 #ifdef B200SP_ROLE_PROFILE
             busy += clock64() - c0;
@@ -685,10 +749,10 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
 #ifdef B200SP_ROLE_PROFILE          // developer builds only (tools/ab_build.sh NAME -DB200SP_ROLE_PROFILE)
         if (P.roleCycles && lane == 0) {
             atomicAdd(&P.roleCycles[role], busy);
-            if (role == 4u) { atomicAdd(&P.roleCycles[5], clock64() - blockStart); atomicAdd(&P.roleCycles[6], (unsigned long long)(nW + 4)); }
+            if (role == 6u) { atomicAdd(&P.roleCycles[7], clock64() - blockStart); atomicAdd(&P.roleCycles[8], (unsigned long long)(nW + 4)); }
         }
 #endif
-        if (role == 4u && lane == 0) {
+        if (role == 6u && lane == 0) {       // the second half's emit warp holds the carry after the last window
             out[ec.nOut] = make_uint4(0u, n - ec.anchor, 0u, 0u);   // trailing literals / block delimiter
             P.counts[b] = ec.nOut + 1u;
         }

@@ -37,14 +37,15 @@ constexpr uint32_t kTmaChunk      = 16384;
 constexpr uint32_t kTmaChunks     = kBlockMax / kTmaChunk;
 
 #ifndef B200SP_EH_WARPS
-#define B200SP_EH_WARPS 28
+#define B200SP_EH_WARPS 26
 #endif
 constexpr int kEhWarps     = B200SP_EH_WARPS;   // hash + extension warps
 constexpr int kWarpTabL    = kEhWarps;          // serial owner of the long-hash table
 constexpr int kWarpTabS    = kEhWarps + 1;      // serial owner of the short-hash table
-constexpr int kWarpEntries = kEhWarps + 2;      // P1: lazy decisions + group entries (speculative, lane-parallel)
-constexpr int kWarpEmit    = kEhWarps + 3;      // P2: scans + ZSTD_Sequence stores
-constexpr int kNumWarps    = kEhWarps + 4;
+constexpr int kWarpEntries = kEhWarps + 2;      // P1 (two warps, one per half window): lazy decisions + group entries
+constexpr int kWarpEmit    = kEhWarps + 4;      // P2 (two warps, one per half window): scans + ZSTD_Sequence stores
+constexpr int kNumWarps    = kEhWarps + 6;
+static_assert(kGroups == 2 * kEhWarps, "two tasks per pool warp and stage");
 constexpr int kThreads     = kNumWarps * 32;
 
 // Shared-memory carve-up (bytes)
