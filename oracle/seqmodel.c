@@ -54,7 +54,7 @@ void seqmodel_params_for_level(int level, SeqModelParams *prm)
 {
     /* One parameter class per zstd strategy class. */
     prm->longBits = 14;
-    prm->shortBits = 14;
+    prm->shortBits = 12;         /* 8 KiB: the kernel spends its shared memory on a wider pipeline window instead */
     prm->shortBytes = 5;
     prm->minMatch = 4;
     prm->extCap = 256;

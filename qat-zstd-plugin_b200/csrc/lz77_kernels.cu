@@ -140,7 +140,7 @@ __device__ __forceinline__ uint32_t pop_task(uint32_t ctrAddr, uint32_t lane)
 // reads the same local position in 32 groups).
 __device__ __forceinline__ uint32_t ring_byte(uint32_t group, uint32_t lane)   // byte offset of a 32-bit ring word
 {
-    return (group * 32u + (lane ^ group)) * 4u;
+    return (group * 32u + (lane ^ (group & 31u))) * 4u;
 }
 
 struct Shared {         // 32-bit shared-window addresses
@@ -157,6 +157,11 @@ struct Shared {         // 32-bit shared-window addresses
     uint32_t mbar;      // u64[kTmaChunks]
     uint32_t work;      // next block index
     uint32_t task;      // u32[2] per-stage task counters of the hash/extend warps (double-buffered)
+    uint32_t curVal;    // entry warps: where the parse enters the next half window ...
+    uint32_t curTag;    // ... and which half that is: 2 * window + half + 1 of the publisher (0 = none yet)
+    uint32_t ecVal;     // emit warps: u32[3] anchor, previous offset, sequences written, after the publisher's half ...
+    uint32_t ecTag;     // ... same numbering
+    uint32_t emTag;     // emit warps: window + 1 once the first half's sequences are in memory
 };
 
 // ------------------------------------------------------------------------------------------
@@ -222,7 +227,8 @@ __device__ __forceinline__ void stage_table(const Shared &S, uint32_t tab, uint3
     for (uint32_t g0 = 0; g0 < kGroups; g0 += 8) {
         uint32_t hw[8], tv[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) hw[k] = (lds32(rh + ring_byte(g0 + k, lane)) >> sh) & 0xFFFFu;
+        for (int k = 0; k < 8; k++)      // groups past the window's end: linked, not last -> no table access below
+            hw[k] = g0 + k < kGroups ? (lds32(rh + ring_byte(g0 + k, lane)) >> sh) & 0xFFFFu : 0x4000u;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const uint32_t ha = tab + (hw[k] & 0x3FFFu) * 2u;
@@ -348,7 +354,7 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32
     }
     sts32(idx, pk);                                      // prefix-max within the group
     const uint32_t own = __ballot_sync(0xFFFFFFFFu, (pk >> 23) >= lane + minMatch);
-    if (lane == 31) { sts32(S.gmax + (slot * kGroups + group) * 4u, pk); sts32(S.gown + (slot * kGroups + group) * 4u, own); }
+    if (lane == 31) { sts32(S.gmax + (slot * 64u + group) * 4u, pk); sts32(S.gown + (slot * 64u + group) * 4u, own); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -380,10 +386,15 @@ __device__ __forceinline__ uint32_t eval_step(uint32_t pkRow, uint32_t group, ui
     return L;
 }
 
-__device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint32_t lane, uint32_t &cursor,
+__device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint32_t half, uint32_t lane,
                                               uint32_t minMatch, uint32_t lazyDepth)
 {
-    const uint32_t slot = w & (kRingC - 1), base = w * kWindow;
+    // Lane j owns group half * kHalf + j of the window.  The two halves of a window are handled by two warps in
+    // the same stage: where the parse enters a half is published by the warp of the half before it (the second
+    // half of the previous window: last stage; the first half of this window: any moment now), tagged
+    // 2 * window + half + 1.
+    const uint32_t slot = w & (kRingC - 1), base = w * kWindow, group = half * kHalf + lane;
+    const bool act = lane < kHalf;
     const uint32_t pkRow = S.ringC + slot * (kWindow * 4u);
     const uint32_t linkRow = S.ringL + (w & 1u) * (kWindow * 4u);
     // ---- carry: farthest-reaching match of the previous 8 groups (a match is at most extCap = 256
@@ -391,19 +402,19 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
     uint32_t c = 0;
 #pragma unroll
     for (uint32_t k = 1; k <= 8; k++) {
-        int gg = static_cast<int>(lane) - static_cast<int>(k);
+        int gg = static_cast<int>(group) - static_cast<int>(k);
         uint32_t sl = slot;
         bool ok = true;
         if (gg < 0) { ok = w > 0; gg += kGroups; sl = (w - 1) & (kRingC - 1); }
-        const uint32_t v = ok ? lds32(S.gmax + (sl * kGroups + gg) * 4u) : 0u;
+        const uint32_t v = ok ? lds32(S.gmax + (sl * 64u + gg) * 4u) : 0u;
         const uint32_t rel = v >> 23;
         if (rel > 32u * k) c = max(c, ((rel - 32u * k) << 23) | ((32u + k) << 17) | (v & 0x1FFFFu));
     }
     const uint32_t cRel = c >> 23;
     uint32_t cover = 0;
     if (cRel >= minMatch) cover = (cRel - minMatch >= 31u) ? 0xFFFFFFFFu : (2u << (cRel - minMatch)) - 1u;
-    const uint32_t has = lds32(S.gown + (slot * kGroups + lane) * 4u) | cover;
-    const uint32_t segStart = base + lane * 32u, segEnd = segStart + 32u;
+    const uint32_t has = act ? lds32(S.gown + (slot * 64u + group) * 4u) | cover : 0u;
+    const uint32_t segStart = base + group * 32u, segEnd = segStart + 32u;
 
     // ---- every lane guesses that the parser enters its group at its first position; the guesses are
     // corrected from lane 0 upward until nothing changes.  A lane whose entry lies beyond its group is
@@ -412,7 +423,13 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
     // starts, and every decision is memoised, so a corrected lane re-evaluates nothing it has seen.
     // First guess: the parse arrives through the carried match (the farthest-reaching one usually is the
     // one the previous groups ended with); any guess converges to the same fixed point.
-    uint32_t entry = lane == 0 ? max(cursor, base) : segStart + min(cRel, 32u);
+    // That includes lane 0: it starts on a guess as well and takes the published cursor as soon as it is there.
+    const uint32_t expect = 2u * w + half;              // tag of the half before this one
+    bool known = expect == 0u;
+    uint32_t cursor = 0;
+    if (!known && lds32(S.curTag) == expect) { __threadfence_block(); cursor = lds32(S.curVal); known = true; }
+    uint32_t entry = (lane == 0 && known) ? max(cursor, segStart) : segStart + min(cRel, 32u);
+    if (!act) entry = 0xFFFFFFFFu;                      // lanes beyond the half stay inert: never live, never change
     uint32_t visited = 0, pm = 0, walked = 0xFFFFFFFFu, exitPos = 0;
     for (;;) {
         if (entry != walked) {                   // a lane whose entry did not change keeps its exit
@@ -424,10 +441,10 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
                 if (!m) { cur = 32u; break; }
                 const uint32_t p0 = __ffs(m) - 1;
                 uint32_t L;
-                if ((visited >> p0) & 1u) L = lds32(linkRow + ring_byte(lane, p0));
+                if ((visited >> p0) & 1u) L = lds32(linkRow + ring_byte(group, p0));
                 else {
-                    L = eval_step(pkRow, lane, p0, c, has, lazyDepth);
-                    sts32(linkRow + ring_byte(lane, p0), L);
+                    L = eval_step(pkRow, group, p0, c, has, lazyDepth);
+                    sts32(linkRow + ring_byte(group, p0), L);
                     visited |= 1u << p0;
                 }
                 cur = (L >> 22) & 0x1FFu;
@@ -442,14 +459,36 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
             if (lane >= static_cast<uint32_t>(d)) pm = max(pm, o);
         }
         const uint32_t prevMax = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
-        const uint32_t want = lane == 0 ? entry : max(prevMax, segStart);
-        const bool changed = want != entry;
+        uint32_t want = (lane == 0 || !act) ? entry : max(prevMax, segStart);
+        bool changed = want != entry;
+        if (!__any_sync(0xFFFFFFFFu, changed)) {
+            if (known) break;
+            // converged on a guessed entry of the half: wait for the real one (warp-uniform spin)
+            while (lds32(S.curTag) != expect) __nanosleep(B200SP_SPIN_NS);
+            __threadfence_block();
+            cursor = lds32(S.curVal);
+            known = true;
+            if (lane == 0) { want = max(cursor, segStart); changed = want != entry; }
+            if (!__any_sync(0xFFFFFFFFu, changed)) break;
+        } else if (!known && lds32(S.curTag) == expect) {       // warp-uniform: every lane reads the same word
+            __threadfence_block();
+            cursor = lds32(S.curVal);
+            known = true;
+            if (lane == 0) want = max(cursor, segStart);
+        }
         entry = want;
-        if (!__any_sync(0xFFFFFFFFu, changed)) break;
     }
-    cursor = max(__shfl_sync(0xFFFFFFFFu, pm, 31), base + kWindow);
-    sts32(S.hasA + ((w & 1u) * kGroups + lane) * 4u, has);
-    sts32(S.entA + ((w & 1u) * kGroups + lane) * 4u, entry);
+    if (act) {
+        sts32(S.hasA + ((w & 1u) * 64u + group) * 4u, has);
+        sts32(S.entA + ((w & 1u) * 64u + group) * 4u, entry);
+    }
+    // publish where the parse enters the next half
+    const uint32_t next = max(__shfl_sync(0xFFFFFFFFu, pm, 31), base + (half + 1u) * (kHalf * 32u));
+    if (lane == 0) {
+        sts32(S.curVal, next);
+        __threadfence_block();
+        sts32(S.curTag, expect + 1u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -461,13 +500,17 @@ struct EmitCarry {           // uniform across the warp, carried from window to 
     uint32_t nOut;           // sequences written so far
 };
 
-__device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t lane, EmitCarry &ec, uint4 *out)
+// The two halves of a window are emitted by two warps in the same stage.  The carry (anchor, previous offset,
+// sequences written) travels through shared memory like the entry cursor: the first half's warp publishes it
+// right after its scans, so the second half's warp - which has done its counting walk meanwhile - waits little.
+__device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t half, uint32_t lane, EmitCarry &ec, uint4 *out)
 {
-    const uint32_t base = w * kWindow;
+    const uint32_t base = w * kWindow, group = half * kHalf + lane;
+    const bool act = lane < kHalf;
     const uint32_t linkRow = S.ringL + (w & 1u) * (kWindow * 4u);
-    const uint32_t has = lds32(S.hasA + ((w & 1u) * kGroups + lane) * 4u);
-    const uint32_t entry = lds32(S.entA + ((w & 1u) * kGroups + lane) * 4u);
-    const uint32_t segStart = base + lane * 32u, segEnd = segStart + 32u;
+    const uint32_t has = act ? lds32(S.hasA + ((w & 1u) * 64u + group) * 4u) : 0u;
+    const uint32_t entry = act ? lds32(S.entA + ((w & 1u) * 64u + group) * 4u) : 0xFFFFFFFFu;
+    const uint32_t segStart = base + group * 32u, segEnd = segStart + 32u;
     const uint32_t cur0 = entry < segEnd ? entry - segStart : 32u;
 
     // ---- counting walk along the memoised links
@@ -477,7 +520,7 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
         while (cur < 32u) {
             const uint32_t m = has & (0xFFFFFFFFu << cur);
             if (!m) break;
-            const uint32_t L = lds32(linkRow + ring_byte(lane, __ffs(m) - 1));
+            const uint32_t L = lds32(linkRow + ring_byte(group, __ffs(m) - 1));
             if (L >> 31) { cur = (L >> 22) & 0x1FFu; continue; }         // hop: a later start is better (lazy)
             const uint32_t p = segStart + ((L >> 17) & 31u), end = segStart + (L >> 22), off = L & 0x1FFFFu;
             if (cnt && p == lastEnd && off == lastOff) merges++;
@@ -487,6 +530,17 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
         }
     }
     __syncwarp();
+
+    // ---- the carry of the half before this one
+    {
+        const uint32_t expect = 2u * w + half;
+        if (expect == 0u) { ec.anchor = 0u; ec.prevOff = 0u; ec.nOut = 0u; }
+        else {
+            while (lds32(S.ecTag) != expect) __nanosleep(B200SP_SPIN_NS);
+            __threadfence_block();
+            ec.anchor = lds32(S.ecVal); ec.prevOff = lds32(S.ecVal + 4u); ec.nOut = lds32(S.ecVal + 8u);
+        }
+    }
 
     // ---- anchor / previous offset at each lane's entry: exclusive "last match" scan
     uint32_t aE = cnt ? lastEnd : 0u, aO = lastOff;
@@ -511,6 +565,13 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
     }
     const uint32_t firstIdx = ec.nOut + incl - fresh;
     const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (totE) { ec.anchor = totE; ec.prevOff = totO; }
+    ec.nOut += total;
+    if (lane == 0) {            // the next half can run its scans while this one emits
+        sts32(S.ecVal, ec.anchor); sts32(S.ecVal + 4u, ec.prevOff); sts32(S.ecVal + 8u, ec.nOut);
+        __threadfence_block();
+        sts32(S.ecTag, 2u * w + half + 1u);
+    }
 
     // ---- emitting walk.  New sequences go to out[firstIdx...]; a leading continuation of an earlier
     // lane's sequence is added to out[firstIdx - 1].matchLength afterwards.
@@ -522,7 +583,7 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
         while (cur < 32u) {
             const uint32_t m = has & (0xFFFFFFFFu << cur);
             if (!m) break;
-            const uint32_t L = lds32(linkRow + ring_byte(lane, __ffs(m) - 1));
+            const uint32_t L = lds32(linkRow + ring_byte(group, __ffs(m) - 1));
             if (L >> 31) { cur = (L >> 22) & 0x1FFu; continue; }         // hop
             const uint32_t p = segStart + ((L >> 17) & 31u), end = segStart + (L >> 22), o = L & 0x1FFFFu;
             const uint32_t lit = p - anchor, len = end - p;
@@ -538,11 +599,18 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
         if (haveOpen) out[outIdx] = make_uint4(openOff, openLit, openLen, 0u);
     }
     __syncwarp();
+    // A continuation is added to a sequence an earlier lane wrote - for the second half possibly a lane of the
+    // first half's warp, which must have stored it before (its stores of earlier windows are a stage old).
+    if (half == 1u) {
+        while (lds32(S.emTag) != w + 1u) __nanosleep(B200SP_SPIN_NS);
+        __threadfence();
+    }
     if (headAdd) atomicAdd(&out[firstIdx - 1].z, headAdd);   // continuation of an earlier lane's sequence
     __syncwarp();
-
-    if (totE) { ec.anchor = totE; ec.prevOff = totO; }
-    ec.nOut += total;
+    if (half == 0u && lane == 0) {
+        __threadfence();
+        sts32(S.emTag, w + 1u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -561,17 +629,22 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         S.ringH = p; p += kSmemRingH;
         S.ringC = p; p += kSmemRingC;
         S.ringL = p; p += kSmemRingL;
-        S.gmax = p;  p += kRingC * kGroups * 4;
-        S.gown = p;  p += kRingC * kGroups * 4;
-        S.hasA = p;  p += 2 * kGroups * 4;
-        S.entA = p;  p += 2 * kGroups * 4;
+        S.gmax = p;  p += kRingC * 64 * 4;
+        S.gown = p;  p += kRingC * 64 * 4;
+        S.hasA = p;  p += 2 * 64 * 4;
+        S.entA = p;  p += 2 * 64 * 4;
         S.mbar = p;  p += kTmaChunks * 8;
         S.work = p;  p += 8;
-        S.task = p;
+        S.task = p;  p += 8;
+        S.curVal = p; p += 4;
+        S.curTag = p; p += 4;
+        S.ecVal = p;  p += 12;
+        S.ecTag = p;  p += 4;
+        S.emTag = p;
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    // Role of this warp: 0 = hash/extend pool, 1 = long table, 2 = short table, 3 = entries (P1), 4 = emit (P2).
-    // (Which scheduler the four serial warps sit on made no measurable difference.)
+    // Role of this warp: 0 = hash/extend pool, 1 = long table, 2 = short table, 3 / 4 = entries of the first /
+    // second half window (P1), 5 / 6 = emit of the first / second half window (P2).
     const uint32_t role = warp < kEhWarps ? 0u : warp - kEhWarps + 1u;
 
     if (tid == 0) {
@@ -615,13 +688,13 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         for (uint32_t i = tid; i < (kSmemTabL + kSmemTabS) / 16; i += kThreads)    // tabL and tabS are contiguous
             sts128(S.tabL + i * 16u, 0xFFFFFFFFu);
         if (tid < 2) sts32(S.task + tid * 4u, kEhWarps);
+        if (tid == 2) { sts32(S.curTag, 0u); sts32(S.ecTag, 0u); sts32(S.emTag, 0u); }
         __syncthreads();
 
         const uint32_t nh = n >= 8 ? n - 7 : 0;
         const uint32_t nW = (n + kWindow - 1) / kWindow;
         uint32_t chunksSeen = 0;
-        uint32_t cursor = 0;                   // P1: first position the parser has not consumed yet
-        EmitCarry ec = {0, 0, 0};              // P2
+        EmitCarry ec = {0, 0, 0};              // P2 (loaded from / published to shared memory every half window)
 
 #ifdef B200SP_ROLE_PROFILE
         unsigned long long busy = 0, blockStart = clock64();
@@ -661,11 +734,11 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabL, 0u, t - 1, lane);
             } else if (role == 2u) {
                 if (t >= 1 && t - 1 < nW) stage_table(S, S.tabS, 1u, t - 1, lane);
-            } else if (role == 3u) {
-                if (lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, kEhWarps);   // next stage's queue (nobody touches it now)
-                if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, lane, cursor, P.minMatch, P.lazyDepth);
+            } else if (role <= 4u) {
+                if (role == 3u && lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, kEhWarps);   // next stage's queue (nobody touches it now)
+                if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, role - 3u, lane, P.minMatch, P.lazyDepth);
             } else {
-                if (t >= 4) stage_emit(S, t - 4, lane, ec, out);
+                if (t >= 4) stage_emit(S, t - 4, role - 5u, lane, ec, out);
             }
 #ifdef B200SP_ROLE_PROFILE
             busy += clock64() - c0;
@@ -676,10 +749,10 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
 #ifdef B200SP_ROLE_PROFILE          // developer builds only (tools/ab_build.sh NAME -DB200SP_ROLE_PROFILE)
         if (P.roleCycles && lane == 0) {
             atomicAdd(&P.roleCycles[role], busy);
-            if (role == 4u) { atomicAdd(&P.roleCycles[5], clock64() - blockStart); atomicAdd(&P.roleCycles[6], (unsigned long long)(nW + 4)); }
+            if (role == 6u) { atomicAdd(&P.roleCycles[7], clock64() - blockStart); atomicAdd(&P.roleCycles[8], (unsigned long long)(nW + 4)); }
         }
 #endif
-        if (role == 4u && lane == 0) {
+        if (role == 6u && lane == 0) {       // the second half's emit warp holds the carry after the last window
             out[ec.nOut] = make_uint4(0u, n - ec.anchor, 0u, 0u);   // trailing literals / block delimiter
             P.counts[b] = ec.nOut + 1u;
         }

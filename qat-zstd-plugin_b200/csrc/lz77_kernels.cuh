@@ -13,11 +13,19 @@
 namespace b200sp {
 
 constexpr uint32_t kBlockMax      = 1u << 17;   // ZSTD_BLOCKSIZE_MAX
-constexpr uint32_t kWindow        = 1024;       // positions per pipeline window
-constexpr uint32_t kGroups        = kWindow / 32;
+#ifndef B200SP_GROUPS
+#define B200SP_GROUPS 52
+#endif
+// A window is one stage's worth of work: kGroups groups of 32 positions = two tasks per pool warp, so that the
+// task queue balances inside a stage (32 tasks on 28 warps made every stage last two tasks with most warps
+// waiting through the second).  The parse warps own one group per lane: they take a window in two halves.
+constexpr uint32_t kGroups        = B200SP_GROUPS;
+constexpr uint32_t kHalf          = kGroups / 2;    // groups per parse pass (<= 32: one lane each)
+constexpr uint32_t kWindow        = kGroups * 32;   // positions per pipeline window
+static_assert(kGroups % 2 == 0 && kHalf >= 9 && kHalf <= 32 && kGroups <= 64, "two parse passes of at most 32 groups; carries look 8 groups back");
 constexpr uint32_t kRingC         = 4;          // candidate/match ring: windows in flight between hash and entries
 constexpr uint32_t kLongBits      = 14;
-constexpr uint32_t kShortBits     = 14;
+constexpr uint32_t kShortBits     = 12;         // 8 KiB: the shared memory the wider window needs comes from here (+1.1 % in size)
 #ifndef B200SP_HASH_GROUPS
 #define B200SP_HASH_GROUPS 1
 #endif
@@ -29,14 +37,15 @@ constexpr uint32_t kTmaChunk      = 16384;
 constexpr uint32_t kTmaChunks     = kBlockMax / kTmaChunk;
 
 #ifndef B200SP_EH_WARPS
-#define B200SP_EH_WARPS 28
+#define B200SP_EH_WARPS 26
 #endif
 constexpr int kEhWarps     = B200SP_EH_WARPS;   // hash + extension warps
 constexpr int kWarpTabL    = kEhWarps;          // serial owner of the long-hash table
 constexpr int kWarpTabS    = kEhWarps + 1;      // serial owner of the short-hash table
-constexpr int kWarpEntries = kEhWarps + 2;      // P1: lazy decisions + group entries (speculative, lane-parallel)
-constexpr int kWarpEmit    = kEhWarps + 3;      // P2: scans + ZSTD_Sequence stores
-constexpr int kNumWarps    = kEhWarps + 4;
+constexpr int kWarpEntries = kEhWarps + 2;      // P1 (two warps, one per half window): lazy decisions + group entries
+constexpr int kWarpEmit    = kEhWarps + 4;      // P2 (two warps, one per half window): scans + ZSTD_Sequence stores
+constexpr int kNumWarps    = kEhWarps + 6;
+static_assert(kGroups == 2 * kEhWarps, "two tasks per pool warp and stage");
 constexpr int kThreads     = kNumWarps * 32;
 
 // Shared-memory carve-up (bytes)
@@ -46,7 +55,7 @@ constexpr uint32_t kSmemTabS    = (1u << kShortBits) * 2;
 constexpr uint32_t kSmemRingH   = 2 * kWindow * 4;        // hash words, H -> T
 constexpr uint32_t kSmemRingC   = kRingC * kWindow * 4;   // candidates -> packed prefix maxima, H/T -> E -> P1
 constexpr uint32_t kSmemRingL   = 2 * kWindow * 4;        // memoised parse decisions, P1 -> P2
-constexpr uint32_t kSmemGroup   = (2 * kRingC + 4) * kGroups * 4;   // gmax, gown, hasA, entA
+constexpr uint32_t kSmemGroup   = (2 * kRingC + 4) * 64 * 4;   // gmax, gown, hasA, entA (64 entries per window)
 constexpr uint32_t kSmemMisc    = 128;          // mbarriers + work-item slot + task counters
 constexpr uint32_t kSmemTotal   = kSmemInput + kSmemTabL + kSmemTabS + kSmemRingH + kSmemRingC + kSmemRingL + kSmemGroup + kSmemMisc;
 static_assert(kSmemTotal <= 232448, "exceeds 227 KB of shared memory per CTA");

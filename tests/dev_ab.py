@@ -48,7 +48,7 @@ def one():
         for _ in range(3): f()
         torch.cuda.synchronize()
         if os.environ.get("B200SP_ROLE_PROFILE"):
-            buf = (ctypes.c_ulonglong * 8)(); pkg.lib.b200sp_debug_role_cycles(eng._h, buf)
+            buf = (ctypes.c_ulonglong * 10)(); pkg.lib.b200sp_debug_role_cycles(eng._h, buf)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10): f()
@@ -56,9 +56,9 @@ def one():
         ms = e0.elapsed_time(e1) / 10
         role = ""
         if os.environ.get("B200SP_ROLE_PROFILE"):
-            buf = (ctypes.c_ulonglong * 8)(); pkg.lib.b200sp_debug_role_cycles(eng._h, buf)
-            r = list(buf); st = max(r[6], 1)
-            role = f" [EH {r[0]/st/28:.0f} TL {r[1]/st:.0f} TS {r[2]/st:.0f} P1 {r[3]/st:.0f} P2 {r[4]/st:.0f} wall {r[5]/st:.0f}]"
+            buf = (ctypes.c_ulonglong * 10)(); pkg.lib.b200sp_debug_role_cycles(eng._h, buf)
+            r = list(buf); st = max(r[8], 1)
+            role = f" [EH {r[0]/st/26:.0f} TL {r[1]/st:.0f} TS {r[2]/st:.0f} P1a {r[3]/st:.0f} P1b {r[4]/st:.0f} P2a {r[5]/st:.0f} P2b {r[6]/st:.0f} wall {r[7]/st:.0f}]"
         out.append(f"L{level} {ms:.3f} ms {len(data)/ms/1e6:.1f} GB/s{role}")
     print(f"{os.path.basename(pkg.LIB_PATH):24s} parity {checked - bad}/{checked}  " + "  ".join(out), flush=True)
 

@@ -27,10 +27,10 @@ def run(name, data, level=3, steps=5):
     ns = int(counts.sum().item())
     if os.environ.get("B200SP_ROLE_PROFILE"):
         import ctypes
-        buf = (ctypes.c_ulonglong * 8)()
+        buf = (ctypes.c_ulonglong * 10)()
         pkg.lib.b200sp_debug_role_cycles(eng._h, buf)
-        r = list(buf); st = max(r[6], 1)
-        print(f"   per-stage cycles: EH-sum {r[0]/st:9.0f} (per warp {r[0]/st/28:7.0f})  TL {r[1]/st:7.0f}  TS {r[2]/st:7.0f}  P1 {r[3]/st:7.0f}  P2 {r[4]/st:7.0f}  wall {r[5]/st:7.0f}")
+        r = list(buf); st = max(r[8], 1)
+        print(f"   per-stage cycles: EH-sum {r[0]/st:9.0f} (per warp {r[0]/st/26:7.0f})  TL {r[1]/st:7.0f}  TS {r[2]/st:7.0f}  P1a {r[3]/st:7.0f}  P1b {r[4]/st:7.0f}  P2a {r[5]/st:7.0f}  P2b {r[6]/st:7.0f}  wall {r[7]/st:7.0f}")
     print(f"{name:28s} L{level} {n/1e6:8.1f} MB {nb:5d} blk  {ms:8.3f} ms  {n/ms/1e6:8.1f} GB/s  seq/blk {ns/nb:8.0f}  us/blk/SM {ms*1e3/(nb/148 if nb>148 else 1):7.1f}", flush=True)
 data, label, info = corpus.load()
 run("image-corpus", data)
