@@ -11,7 +11,7 @@
  *       the matches starting in its group  {end - groupStart : 9 | 31 - lane : 6 | offset : 17},
  *       per group the maximum of the whole group (gmax) and the mask of positions whose own prefix
  *       maximum is a usable match (gown).
- *   P1 (one warp, lane j = group j of a 1024-position window):
+ *   P1 (lane j = group j of a half window of KGPW groups; one warp per half, both in the same stage):
  *       carry  c_j   = farthest-reaching match of the previous 8 groups, re-based to group j;
  *       B(p)         = max(prefix maximum at p, c_j);   has_j = gown_j | {lanes covered by c_j};
  *       walk(e)      = greedy/lazy parse of group j entered at e; every decision is memoised as a link
@@ -27,8 +27,9 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define KWIN    1024u
-#define KGRP    32u
+#define KGRP    32u               /* positions per group (one warp's worth) */
+#define KGPW    26u               /* groups per parse pass = lanes of a parse warp in use (kHalf of the kernel) */
+#define KWIN    (KGPW * KGRP)     /* positions per parse pass (half a pipeline window) */
 
 static inline uint32_t umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
 static inline uint32_t floorlog2(uint32_t v) { return 31u - (uint32_t)__builtin_clz(v); }
@@ -81,7 +82,7 @@ size_t lanemodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t 
     if (n > (1u << 17) || outCap == 0 || prm->window != (int)KGRP) return (size_t)-1;
     const uint32_t N = (uint32_t)n;
     const uint32_t nW = (N + KWIN - 1) / KWIN;
-    const uint32_t nG = nW * KGRP;
+    const uint32_t nG = nW * KGPW;
     const uint32_t minMatch = (uint32_t)prm->minMatch;
     uint32_t *ownLen = (uint32_t *)calloc(nW * KWIN + 1, sizeof(uint32_t));
     uint32_t *ownOff = (uint32_t *)calloc(nW * KWIN + 1, sizeof(uint32_t));
@@ -114,10 +115,10 @@ size_t lanemodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t 
     uint32_t cursor = 0;
     for (uint32_t w = 0; w < nW; w++) {
         const uint32_t base = w * KWIN;
-        Group g[KGRP];
-        uint32_t entry[KGRP], exitPos[KGRP], pm[KGRP];
-        for (uint32_t j = 0; j < KGRP; j++) {
-            const uint32_t G = w * KGRP + j;
+        Group g[KGPW];
+        uint32_t entry[KGPW], exitPos[KGPW], pm[KGPW];
+        for (uint32_t j = 0; j < KGPW; j++) {
+            const uint32_t G = w * KGPW + j;
             uint32_t c = 0;
             for (uint32_t k = 1; k <= 8 && k <= G; k++) {
                 const uint32_t v = gmax[G - k], rel = v >> 23;
@@ -133,25 +134,25 @@ size_t lanemodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t 
             entry[j] = j == 0 ? umax(cursor, base) : base + j * KGRP + (cRel < KGRP ? cRel : KGRP);
         }
         for (;;) {
-            for (uint32_t j = 0; j < KGRP; j++) {
+            for (uint32_t j = 0; j < KGPW; j++) {
                 const uint32_t segStart = base + j * KGRP, segEnd = segStart + KGRP;
                 const int live = entry[j] < segEnd;
                 exitPos[j] = live ? segStart + walk_exit(&g[j], entry[j] - segStart) : 0u;
             }
             uint32_t run = 0;
-            for (uint32_t j = 0; j < KGRP; j++) {           /* inclusive prefix maximum */
+            for (uint32_t j = 0; j < KGPW; j++) {           /* inclusive prefix maximum */
                 run = umax(run, j == 0 ? umax(exitPos[0], entry[0]) : exitPos[j]);
                 pm[j] = run;
             }
             int changed = 0;
-            for (uint32_t j = 1; j < KGRP; j++) {
+            for (uint32_t j = 1; j < KGPW; j++) {
                 const uint32_t want = umax(pm[j - 1], base + j * KGRP);
                 if (want != entry[j]) { entry[j] = want; changed = 1; }
             }
             if (!changed) break;
         }
-        cursor = umax(pm[KGRP - 1], base + KWIN);
-        for (uint32_t j = 0; j < KGRP; j++) { hasA[w * KGRP + j] = g[j].has; entA[w * KGRP + j] = entry[j]; }
+        cursor = umax(pm[KGPW - 1], base + KWIN);
+        for (uint32_t j = 0; j < KGPW; j++) { hasA[w * KGPW + j] = g[j].has; entA[w * KGPW + j] = entry[j]; }
     }
 
     /* ---- P2: follow the links from the final entries, scan, emit */
@@ -160,9 +161,9 @@ size_t lanemodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t 
         size_t nOut = 0;
         for (uint32_t w = 0; w < nW; w++) {
             const uint32_t base = w * KWIN;
-            uint32_t cnt[KGRP], merges[KGRP], firstPos[KGRP], firstOff[KGRP], lastEnd[KGRP], lastOff[KGRP];
-            for (uint32_t j = 0; j < KGRP; j++) {            /* counting walk */
-                const uint32_t G = w * KGRP + j, segStart = base + j * KGRP;
+            uint32_t cnt[KGPW], merges[KGPW], firstPos[KGPW], firstOff[KGPW], lastEnd[KGPW], lastOff[KGPW];
+            for (uint32_t j = 0; j < KGPW; j++) {            /* counting walk */
+                const uint32_t G = w * KGPW + j, segStart = base + j * KGRP;
                 cnt[j] = merges[j] = firstPos[j] = firstOff[j] = lastEnd[j] = lastOff[j] = 0;
                 uint32_t cur = entA[G] - segStart;           /* >= 32 (or wrapped huge) when passed over */
                 if (entA[G] < segStart) goto done;           /* cannot happen */
@@ -181,8 +182,8 @@ size_t lanemodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t 
             /* exclusive "last match" scan, head merges, output slots */
             uint32_t runE = anchorC, runO = prevOffC;
             size_t idx = nOut;
-            for (uint32_t j = 0; j < KGRP; j++) {
-                const uint32_t G = w * KGRP + j, segStart = base + j * KGRP;
+            for (uint32_t j = 0; j < KGPW; j++) {
+                const uint32_t G = w * KGPW + j, segStart = base + j * KGRP;
                 uint32_t anchor = runE, prevOff = runO;
                 const int headMerge = cnt[j] && firstPos[j] == anchor && firstOff[j] == prevOff && anchor > 0;
                 /* emitting walk: new entries start at the slot the scan assigned to this lane */

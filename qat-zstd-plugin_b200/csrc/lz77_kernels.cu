@@ -453,8 +453,9 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
         }
         __syncwarp();
         pm = lane == 0 ? max(exitPos, entry) : exitPos;              // lane 0 also carries the window's entry cursor
+        // an exit lies at most 9 groups ahead (32 + extCap + 32 bytes): a maximum over the previous 15 lanes is enough
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
+        for (int d = 1; d < 16; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pm, d);
             if (lane >= static_cast<uint32_t>(d)) pm = max(pm, o);
         }
