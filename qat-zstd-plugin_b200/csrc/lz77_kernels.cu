@@ -10,18 +10,20 @@
  * One persistent CTA per SM; a CTA owns one block at a time:
  *   - the block is staged into shared memory with 1-D TMA bulk copies (UBLKCP), 16 KiB per
  *     mbarrier so the pipeline starts before the whole block has landed;
- *   - both hash tables (2 x 16 Ki x u16, positions stored >> 1) live in shared memory;
- *   - the block flows through rings of 1024-position windows, one role per stage time t:
- *       H  hash     window t    28 warps (shared queue with E)  8-byte + short hash per position,
- *                               intra-warp duplicate links resolved on the spot (match.any)
+ *   - both hash tables (16 Ki + 4 Ki x u16, positions stored >> 1) live in shared memory;
+ *   - the block flows through rings of windows (52 groups of 32 positions), one role per stage time t:
+ *       pool        26 warps    one queue of 52 fused tasks per stage (two per warp): task g probes both
+ *                               candidates of group g of window t-2 on 16 bytes, extends long matches
+ *                               warp-cooperatively and leaves the packed prefix maximum of match ends, and -
+ *                               inside its probe block, hidden behind the candidate loads - hashes group g of
+ *                               window t (8-byte + short hash, intra-warp duplicate links by MATCH.ANY)
  *       T  table    window t-1   2 warps  one warp per table walks the window in order: read slot,
  *                               overwrite with the newer position (exact serial semantics)
- *       E  extend   window t-2  28 warps  probe both candidates on 16 bytes, warp-cooperative long
- *                               extension, packed prefix maximum of match ends per 32-position group
- *       P1 entries  window t-3   1 warp   lane = group: carry of the previous 8 groups, lazy decisions
- *                               memoised as link words, group entries iterated to the serial fixed point
- *       P2 emit     window t-4   1 warp   lane = group: follow the links, scans for anchors / output
- *                               slots, 16-byte ZSTD_Sequence stores
+ *       P1 entries  window t-3   2 warps  (one per half window) lane = group: carry of the previous 8 groups,
+ *                               lazy decisions memoised as link words, group entries iterated to the serial
+ *                               fixed point; the entry of the second half is handed over through shared memory
+ *       P2 emit     window t-4   2 warps  (one per half window) lane = group: follow the links, scans for
+ *                               anchors / output slots, 16-byte ZSTD_Sequence stores; carry handed over likewise
  * The result is bit-identical to oracle/seqmodel.c (the serial statement); oracle/lanemodel.c states
  * the P1/P2 formulation lane by lane on the CPU.  Integer/indexing work only: no tensor cores, no TMEM.
  */
