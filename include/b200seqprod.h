@@ -97,6 +97,13 @@ typedef struct {
 int b200sp_parse_host(b200sp_engine *engine, const void *h_src, size_t srcSize, uint32_t blockSize,
                       int level, b200sp_result *result);
 
+/* Host-resident batch of SCATTERED blocks (one pointer and one size <= 128 KiB per block), synchronous:
+ * what a dispatcher that coalesces the single-block calls of many threads submits - the analogue of
+ * several threads sharing the QAT instances (QZSTD_grabInstance, :905-933).  Blocks are gathered into
+ * pinned staging at a 128 KiB stride, parsed in one launch, and returned like b200sp_parse_host. */
+int b200sp_parse_blocks(b200sp_engine *engine, const void *const *h_blocks, const uint32_t *sizes,
+                        uint32_t nBlocks, int level, b200sp_result *result);
+
 /* Wire format -> ZSTD_Sequence[] (rep = 0). */
 void b200sp_expand(const uint64_t *packed, size_t count, b200sp_sequence *out);
 

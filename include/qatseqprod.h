@@ -96,6 +96,14 @@ void QZSTD_hintSource(void *sequenceProducerState, const void *src, size_t srcSi
 void QZSTD_getStats(const void *sequenceProducerState, unsigned long long *calls,
                     unsigned long long *errors, unsigned long long *batched);
 
+/* Cross-thread coalescing (additive, optional, off by default; also switched on by the environment variable
+ * QZSTD_COALESCE=1 at QZSTD_startQatDevice).  libzstd hands the producer one block per call; with many
+ * application threads, each with its own CCtx and state, a process-wide dispatcher gathers whatever single-block
+ * calls are pending and parses them in ONE GPU batch - the role the shared instance pool plays in the reference
+ * (QZSTD_grabInstance).  Calls covered by a QZSTD_hintSource batch are not affected.  Returns the previous
+ * setting.  Switch it before the compression threads start. */
+int QZSTD_setCoalescing(int enable);
+
 /* Whole-buffer counterpart of stock ZSTD_generateSequences(): parses ALL blocks of [src, src + srcSize)
  * (blockSize bytes each, 0 = 128 KiB, blocks independent of each other) in one GPU batch and writes one
  * ZSTD_Sequence array in which every block ends with its {0, trailing literals, 0} entry, i.e. the

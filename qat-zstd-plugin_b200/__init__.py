@@ -81,6 +81,8 @@ def _load():
     l.QZSTD_getStats.restype = None
     l.QZSTD_generateSequences.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int]
     l.QZSTD_generateSequences.restype = c_size_t
+    l.QZSTD_setCoalescing.argtypes = [c_int]
+    l.QZSTD_setCoalescing.restype = c_int
     # --- b200seqprod.h
     l.b200sp_driver_device_count.restype = c_int
     l.b200sp_device_count.restype = c_int
@@ -113,6 +115,7 @@ lib = _load()
 EXPORTED_SYMBOLS = [
     "QZSTD_version", "QZSTD_startQatDevice", "QZSTD_stopQatDevice", "QZSTD_createSeqProdState",
     "QZSTD_freeSeqProdState", "qatSequenceProducer", "QZSTD_hintSource", "QZSTD_getStats", "QZSTD_generateSequences",
+    "QZSTD_setCoalescing", "b200sp_parse_blocks",
     "b200sp_driver_device_count", "b200sp_device_count", "b200sp_warmup", "b200sp_engine_create", "b200sp_engine_destroy",
     "b200sp_engine_device", "b200sp_engine_sm_count", "b200sp_parse_device", "b200sp_sync",
     "b200sp_parse_host", "b200sp_expand", "b200sp_verify_device", "b200sp_error_string", "b200sp_version",
@@ -227,6 +230,11 @@ class QatSeqProd:
         a, b, c = c_ulonglong(), c_ulonglong(), c_ulonglong()
         lib.QZSTD_getStats(state, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
         return {"calls": a.value, "errors": b.value, "batched": c.value}
+
+    @staticmethod
+    def setCoalescing(enable: bool) -> bool:
+        """Cross-thread coalescing of single-block calls (process-wide); returns the previous setting."""
+        return bool(lib.QZSTD_setCoalescing(1 if enable else 0))
 
     @staticmethod
     def generateSequences(state: int, data, level: int = 3, block_size: int = 0):

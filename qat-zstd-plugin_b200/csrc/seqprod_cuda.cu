@@ -517,6 +517,72 @@ int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint3
     return B200SP_OK;
 }
 
+int b200sp_parse_blocks(b200sp_engine *e, const void *const *h_blocks, const uint32_t *sizes, uint32_t nBlocks,
+                        int level, b200sp_result *res)
+{
+    if (!e || !res) return fail(B200SP_EINVAL, "null engine/result");
+    memset(res, 0, sizeof *res);
+    if (level < 1 || level > 12) return fail(B200SP_EINVAL, "compression level outside 1..12");
+    if (nBlocks == 0) return B200SP_OK;
+    if (!h_blocks || !sizes) return fail(B200SP_EINVAL, "null block list");
+    for (uint32_t b = 0; b < nBlocks; b++)
+        if (!h_blocks[b] || sizes[b] == 0 || sizes[b] > B200SP_BLOCK_MAX) return fail(B200SP_EINVAL, "block size must be 1..131072");
+    CU_TRY(cudaSetDevice(e->device), "cudaSetDevice");
+
+    const uint64_t stride = B200SP_BLOCK_MAX;
+    const size_t seqStride = B200SP_SEQ_STRIDE, perBlockWorst = B200SP_BLOCK_MAX / 4 + 2;
+    const size_t sizesBytes = (static_cast<size_t>(nBlocks) * sizeof(uint32_t) + 15u) & ~static_cast<size_t>(15);
+    CU_TRY(grow_dev(e->d_src, e->d_srcCap, nBlocks * stride + sizesBytes + 16), "cudaMalloc(src)");
+    CU_TRY(grow_dev(e->d_seqs, e->d_seqsCap, nBlocks * seqStride), "cudaMalloc(seqs)");
+    CU_TRY(grow_dev(e->d_counts, e->d_countsCap, nBlocks), "cudaMalloc(counts)");
+    CU_TRY(grow_dev(e->d_offsets, e->d_offsetsCap, nBlocks + kMaxChunks), "cudaMalloc(offsets)");
+    CU_TRY(grow_dev(e->d_packed, e->d_packedCap, nBlocks * perBlockWorst), "cudaMalloc(packed)");
+    CU_TRY(grow_host(e->h_stage, e->h_stageCap, nBlocks * stride + sizesBytes), "cudaMallocHost(stage)");
+    CU_TRY(grow_host(e->h_counts, e->h_countsCap, nBlocks), "cudaMallocHost(counts)");
+    CU_TRY(grow_host(e->h_offsets, e->h_offsetsCap, nBlocks + kMaxChunks), "cudaMallocHost(offsets)");
+    if (e->h_goffsetsCap < nBlocks + 1) {
+        free(e->h_goffsets);
+        e->h_goffsets = static_cast<unsigned long long *>(malloc((nBlocks + 1 + nBlocks / 4) * sizeof(unsigned long long)));
+        if (!e->h_goffsets) { e->h_goffsetsCap = 0; return fail(B200SP_ENOMEM, "out of host memory"); }
+        e->h_goffsetsCap = nBlocks + 1 + nBlocks / 4;
+    }
+
+    // gather: sizes first (so one copy moves both), then the blocks at a fixed stride; only the bytes of
+    // each block travel
+    uint32_t *hSizes = reinterpret_cast<uint32_t *>(e->h_stage);
+    uint8_t *hBlocks = e->h_stage + sizesBytes;
+    uint8_t *dSizes = e->d_src, *dBlocks = e->d_src + sizesBytes;
+    cudaStream_t st = e->stream;
+    memcpy(hSizes, sizes, nBlocks * sizeof(uint32_t));
+    CU_TRY(cudaMemcpyAsync(dSizes, hSizes, nBlocks * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D sizes");
+    for (uint32_t b = 0; b < nBlocks; b++) {
+        memcpy(hBlocks + b * stride, h_blocks[b], sizes[b]);
+        CU_TRY(cudaMemcpyAsync(dBlocks + b * stride, hBlocks + b * stride, sizes[b], cudaMemcpyHostToDevice, st), "H2D block");
+    }
+    int rc = launch_batch(e, dBlocks, static_cast<uint64_t>(nBlocks) * stride, B200SP_BLOCK_MAX, stride,
+                          reinterpret_cast<const uint32_t *>(dSizes), nBlocks, level,
+                          reinterpret_cast<b200sp_sequence *>(e->d_seqs), seqStride, e->d_counts, st, e->d_work);
+    if (rc) return rc;
+    scan_counts_kernel<<<1, 32, 0, st>>>(e->d_counts, nBlocks, e->d_offsets);
+    CU_TRY(cudaGetLastError(), "launch scan_counts_kernel");
+    pack_kernel<<<e->numSMs * 2, kPostThreads, 0, st>>>(e->d_seqs, seqStride, e->d_counts, e->d_offsets, nBlocks, e->d_packed);
+    CU_TRY(cudaGetLastError(), "launch pack_kernel");
+    CU_TRY(cudaMemcpyAsync(e->h_counts, e->d_counts, nBlocks * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H counts");
+    CU_TRY(cudaMemcpyAsync(e->h_offsets, e->d_offsets, (nBlocks + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "D2H offsets");
+    CU_TRY(cudaStreamSynchronize(st), "sync after parse");
+    const size_t total = static_cast<size_t>(e->h_offsets[nBlocks]);
+    CU_TRY(grow_host(e->h_packed, e->h_packedCap, total + 1024), "cudaMallocHost(packed)");
+    CU_TRY(cudaMemcpyAsync(e->h_packed, e->d_packed, total * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "D2H packed");
+    for (uint32_t b = 0; b <= nBlocks; b++) e->h_goffsets[b] = e->h_offsets[b];
+    CU_TRY(cudaStreamSynchronize(st), "sync after D2H");
+
+    res->nBlocks = nBlocks;
+    res->counts = e->h_counts;
+    res->offsets = reinterpret_cast<const uint64_t *>(e->h_goffsets);
+    res->packed = reinterpret_cast<const uint64_t *>(e->h_packed);
+    return B200SP_OK;
+}
+
 void b200sp_expand(const uint64_t *packed, size_t count, b200sp_sequence *out)
 {
     for (size_t i = 0; i < count; i++) {

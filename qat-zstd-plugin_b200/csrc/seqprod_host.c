@@ -35,6 +35,10 @@ typedef struct {
 
 static QZSTD_Process_T g_process = { QZSTD_FAIL, PTHREAD_MUTEX_INITIALIZER };
 
+static void coalesce_start_if_wanted(void);     /* cross-thread coalescing, further down */
+static void coalesce_stop(void);
+static void coalesce_enable_from_env(void);
+
 typedef struct {
     b200sp_engine *engine;          /* lazily created on the first offloaded block */
     unsigned int failOffloadCnt;    /* blocks refused while the device is down (:1141) */
@@ -93,11 +97,16 @@ int QZSTD_startQatDevice(void)
     status = g_process.status;
     QZSTD_LOG(2, "InitStatus: %d\n", status);
     pthread_mutex_unlock(&g_process.mutex);
+    if (status == QZSTD_OK) {
+        coalesce_enable_from_env();
+        coalesce_start_if_wanted();
+    }
     return status;
 }
 
 void QZSTD_stopQatDevice(void)
 {
+    coalesce_stop();                /* pending single-block calls are refused (ERROR -> software fallback) */
     pthread_mutex_lock(&g_process.mutex);
     g_process.status = QZSTD_FAIL;
     pthread_mutex_unlock(&g_process.mutex);
@@ -144,6 +153,151 @@ static size_t producer_error(QZSTD_State_T *s)
 {
     if (s) s->errors++;
     return ZSTD_SEQUENCE_PRODUCER_ERROR;
+}
+
+/* ---- cross-thread coalescing: a dispatcher parses the pending single-block calls of all threads in one batch ---- */
+#define COALESCE_MAX_BATCH 1024
+
+typedef struct QZSTD_Request {
+    const void *src;
+    uint32_t size;
+    int level;
+    ZSTD_Sequence *out;
+    size_t cap;
+    size_t rc;                      /* result: count or ZSTD_SEQUENCE_PRODUCER_ERROR */
+    int done;
+    struct QZSTD_Request *next;
+} QZSTD_Request;
+
+static struct {
+    pthread_mutex_t mu;
+    pthread_cond_t wake;            /* dispatcher: work arrived or stop requested */
+    pthread_cond_t finished;        /* requesters: some batch finished (broadcast) */
+    QZSTD_Request *head, *tail;
+    int enabled;                    /* requested by QZSTD_setCoalescing / QZSTD_COALESCE */
+    int running;                    /* dispatcher thread alive */
+    int stop;
+    pthread_t thread;
+    unsigned long long batches, blocks;
+} g_co = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, NULL, 0, 0, 0, 0, 0, 0 };
+
+static void *coalesce_main(void *arg)
+{
+    b200sp_engine *engine = NULL;
+    const void **ptrs = (const void **)malloc(COALESCE_MAX_BATCH * sizeof(void *));
+    uint32_t *sizes = (uint32_t *)malloc(COALESCE_MAX_BATCH * sizeof(uint32_t));
+    QZSTD_Request **reqs = (QZSTD_Request **)malloc(COALESCE_MAX_BATCH * sizeof(QZSTD_Request *));
+    int healthy = ptrs && sizes && reqs && b200sp_engine_create(0, &engine) == B200SP_OK;
+    (void)arg;
+    pthread_mutex_lock(&g_co.mu);
+    for (;;) {
+        uint32_t n = 0, i;
+        int level;
+        b200sp_result res;
+        int ok;
+        while (!g_co.head && !g_co.stop) pthread_cond_wait(&g_co.wake, &g_co.mu);
+        if (!g_co.head && g_co.stop) break;
+        /* take the pending requests of the head's level, in arrival order */
+        level = g_co.head->level;
+        {
+            QZSTD_Request **link = &g_co.head, *t;
+            while (*link && n < COALESCE_MAX_BATCH) {
+                QZSTD_Request *r = *link;
+                if (r->level == level) { *link = r->next; reqs[n++] = r; }
+                else link = &r->next;
+            }
+            g_co.tail = NULL;                       /* requests of other levels (or beyond the batch limit) stay queued */
+            for (t = g_co.head; t; t = t->next) g_co.tail = t;
+        }
+        pthread_mutex_unlock(&g_co.mu);
+
+        for (i = 0; i < n; i++) { ptrs[i] = reqs[i]->src; sizes[i] = reqs[i]->size; }
+        ok = healthy && b200sp_parse_blocks(engine, ptrs, sizes, n, level, &res) == B200SP_OK && res.nBlocks == n;
+        if (!ok) QZSTD_LOG(1, "Coalesced parse failed: %s\n", b200sp_error_string());
+        for (i = 0; i < n; i++) {
+            QZSTD_Request *r = reqs[i];
+            size_t rc = ZSTD_SEQUENCE_PRODUCER_ERROR;
+            if (ok) {
+                rc = res.counts[i];
+                if (rc >= r->cap - 1) rc = ZSTD_SEQUENCE_PRODUCER_ERROR;        /* same guard as the reference (:1318-1322) */
+                else b200sp_expand(res.packed + res.offsets[i], rc, (b200sp_sequence *)r->out);
+            }
+            r->rc = rc;
+        }
+        pthread_mutex_lock(&g_co.mu);
+        for (i = 0; i < n; i++) reqs[i]->done = 1;
+        g_co.batches++; g_co.blocks += n;
+        pthread_cond_broadcast(&g_co.finished);
+    }
+    /* stop: whatever is still queued is refused */
+    while (g_co.head) { QZSTD_Request *r = g_co.head; g_co.head = r->next; r->rc = ZSTD_SEQUENCE_PRODUCER_ERROR; r->done = 1; }
+    g_co.tail = NULL;
+    g_co.running = 0;
+    pthread_cond_broadcast(&g_co.finished);
+    pthread_mutex_unlock(&g_co.mu);
+    if (engine) b200sp_engine_destroy(engine);
+    free(ptrs); free(sizes); free(reqs);
+    return NULL;
+}
+
+/* Starts the dispatcher if coalescing is wanted and the device is up.  Caller holds no lock. */
+static void coalesce_start_if_wanted(void)
+{
+    pthread_mutex_lock(&g_co.mu);
+    if (g_co.enabled && !g_co.running && g_process.status == QZSTD_OK) {
+        g_co.stop = 0;
+        if (pthread_create(&g_co.thread, NULL, coalesce_main, NULL) == 0) g_co.running = 1;
+    }
+    pthread_mutex_unlock(&g_co.mu);
+}
+
+static void coalesce_stop(void)
+{
+    pthread_t th;
+    int join = 0;
+    pthread_mutex_lock(&g_co.mu);
+    if (g_co.running) { g_co.stop = 1; th = g_co.thread; join = 1; pthread_cond_signal(&g_co.wake); }
+    pthread_mutex_unlock(&g_co.mu);
+    if (join) pthread_join(th, NULL);
+}
+
+/* One block through the dispatcher.  Returns 0 and *rc when it was handled there, -1 when coalescing is off. */
+static int coalesce_submit(const void *src, size_t srcSize, int level, ZSTD_Sequence *out, size_t cap, size_t *rc)
+{
+    QZSTD_Request r;
+    pthread_mutex_lock(&g_co.mu);
+    if (!g_co.running || g_co.stop) { pthread_mutex_unlock(&g_co.mu); return -1; }
+    r.src = src; r.size = (uint32_t)srcSize; r.level = level; r.out = out; r.cap = cap;
+    r.rc = ZSTD_SEQUENCE_PRODUCER_ERROR; r.done = 0; r.next = NULL;
+    if (g_co.tail) g_co.tail->next = &r; else g_co.head = &r;
+    g_co.tail = &r;
+    pthread_cond_signal(&g_co.wake);
+    while (!r.done) pthread_cond_wait(&g_co.finished, &g_co.mu);
+    pthread_mutex_unlock(&g_co.mu);
+    *rc = r.rc;
+    return 0;
+}
+
+static void coalesce_enable_from_env(void)
+{
+    const char *e = getenv("QZSTD_COALESCE");
+    if (e && *e && *e != '0') {
+        pthread_mutex_lock(&g_co.mu);
+        g_co.enabled = 1;
+        pthread_mutex_unlock(&g_co.mu);
+    }
+}
+
+int QZSTD_setCoalescing(int enable)
+{
+    int before;
+    pthread_mutex_lock(&g_co.mu);
+    before = g_co.enabled;
+    g_co.enabled = enable ? 1 : 0;
+    pthread_mutex_unlock(&g_co.mu);
+    if (enable) coalesce_start_if_wanted();
+    else coalesce_stop();
+    return before;
 }
 
 /* device status: fail fast, retry the start every 1000th refused block (:1140-1152); then make sure the
@@ -228,6 +382,13 @@ size_t qatSequenceProducer(
                 }
             }
         }
+    }
+
+    /* many threads, one block each: let the dispatcher batch them (optional) */
+    if (coalesce_submit(src, srcSize, compressionLevel, outSeqs, outSeqsCapacity, &rc) == 0) {
+        if (rc == ZSTD_SEQUENCE_PRODUCER_ERROR) return producer_error(s);
+        s->batched++;
+        return rc;
     }
 
     /* batch of one block */

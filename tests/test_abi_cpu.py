@@ -194,3 +194,22 @@ def test_compress_sequences_hand_off_format(oracle):
     bad[5, 0] += 1                                # a wrong offset must not survive validation + round trip
     r2 = oracle.compress_sequences(data, bad, level=3)
     assert not r2["round_trip"]
+
+
+@pytest.mark.skipif(gpu_present(), reason="no-device behaviour; covered by the gpu tests on a B200")
+def test_coalescing_switch_without_device(pkg):
+    """QZSTD_setCoalescing is a process-wide switch; without a device no dispatcher starts and the producer keeps
+    answering ERROR (software fallback), and stop/start stay idempotent."""
+    q = pkg.QatSeqProd
+    assert q.setCoalescing(True) is False
+    assert q.setCoalescing(True) is True
+    assert q.startQatDevice() == pkg.QZSTD_FAIL
+    st = q.createSeqProdState()
+    src = np.zeros(4096, np.uint8)
+    out = np.zeros((2000, 4), np.uint32)
+    assert q.qatSequenceProducer(st, out.ctypes.data, 2000, src.ctypes.data, src.size, None, 0, 3, 1 << 17) == \
+        pkg.ZSTD_SEQUENCE_PRODUCER_ERROR
+    q.freeSeqProdState(st)
+    q.stopQatDevice()
+    assert q.setCoalescing(False) is True
+    assert q.setCoalescing(False) is False

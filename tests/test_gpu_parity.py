@@ -248,3 +248,39 @@ def test_parse_host_many_blocks_and_pageable_input(pkg, oracle, engine):
             assert got.shape == want.shape and (got == want).all(), f"block {b} of {nb} (block size {bs})"
         total = sum(int(seqs[int(offsets[b]):int(offsets[b + 1]), 1:3].sum()) for b in (0, nb // 2, nb - 1))
         assert total == sum(len(part[b * bs:(b + 1) * bs]) for b in (0, nb // 2, nb - 1))
+
+
+def test_cross_thread_coalescing(pkg, oracle):
+    """SURVEY 7.3 "cross-thread coalescing": with QZSTD_setCoalescing(1) the single-block calls of many threads
+    are gathered by a dispatcher and parsed in one GPU batch (b200sp_parse_blocks).  Eight threads compress
+    different buffers; every frame equals the one the uncoalesced path produces, round-trips, no producer error,
+    and the calls were served by the dispatcher."""
+    import threading
+    q = pkg.QatSeqProd
+    bufs = [datagen.mixed_corpus(3 * BLOCK + 500 * (i + 1), seed=80 + i) for i in range(8)]
+    assert q.startQatDevice() == pkg.QZSTD_OK
+    st0 = q.createSeqProdState()
+    ref = [oracle.compress_with_producer(b, q.producer, st0, chunk=BLOCK, level=3 + (i % 2) * 3)["csize"] for i, b in enumerate(bufs)]
+    assert q.getStats(st0)["batched"] == 0
+    q.freeSeqProdState(st0)
+    assert q.setCoalescing(True) is False
+    out, stats = [None] * 8, [None] * 8
+
+    def work(i):
+        st = q.createSeqProdState()
+        try:
+            for _ in range(2):
+                out[i] = oracle.compress_with_producer(bufs[i], q.producer, st, chunk=BLOCK, level=3 + (i % 2) * 3)
+            stats[i] = q.getStats(st)
+        finally:
+            q.freeSeqProdState(st)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    for t in ts: t.start()
+    for t in ts: t.join()
+    assert q.setCoalescing(False) is True
+    q.stopQatDevice()
+    for i in range(8):
+        assert out[i] is not None and out[i]["round_trip"] and out[i]["errors"] == 0
+        assert out[i]["csize"] == ref[i]
+        assert stats[i]["batched"] == stats[i]["calls"] > 0          # every block went through the dispatcher
