@@ -213,3 +213,18 @@ def test_coalescing_switch_without_device(pkg):
     q.stopQatDevice()
     assert q.setCoalescing(False) is True
     assert q.setCoalescing(False) is False
+
+
+def test_c_abi_argument_checks_without_device(pkg):
+    """Entry points of include/b200seqprod.h reject bad arguments with B200SP_EINVAL before touching a device."""
+    lib = pkg.lib
+    lib.b200sp_parse_blocks.restype = ctypes.c_int
+    lib.b200sp_parse_host.restype = ctypes.c_int
+    lib.b200sp_warmup.restype = ctypes.c_int
+    EINVAL = -3
+    assert lib.b200sp_parse_blocks(None, None, None, 1, 3, None) == EINVAL
+    assert lib.b200sp_parse_host(None, None, 0, 131072, 3, None) == EINVAL
+    assert lib.b200sp_sync(None) == EINVAL
+    if not gpu_present():
+        assert lib.b200sp_warmup(0) in (-1, -2)            # no device / unsupported device
+        assert lib.b200sp_error_string()
