@@ -104,6 +104,14 @@ int b200sp_parse_host(b200sp_engine *engine, const void *h_src, size_t srcSize, 
 int b200sp_parse_blocks(b200sp_engine *engine, const void *const *h_blocks, const uint32_t *sizes,
                         uint32_t nBlocks, int level, b200sp_result *result);
 
+/* The two halves of b200sp_parse_blocks, for callers whose threads copy their own blocks in parallel:
+ * b200sp_stage_reserve returns the engine's pinned staging area for nSlots blocks (slot k at offset
+ * k * 128 KiB; the address is stable until a larger reservation is made); b200sp_parse_staged parses the first
+ * nBlocks slots, sizes[k] bytes each. */
+int b200sp_stage_reserve(b200sp_engine *engine, uint32_t nSlots, void **slots);
+int b200sp_parse_staged(b200sp_engine *engine, const uint32_t *sizes, uint32_t nBlocks, int level,
+                        b200sp_result *result);
+
 /* Wire format -> ZSTD_Sequence[] (rep = 0). */
 void b200sp_expand(const uint64_t *packed, size_t count, b200sp_sequence *out);
 

@@ -115,7 +115,7 @@ lib = _load()
 EXPORTED_SYMBOLS = [
     "QZSTD_version", "QZSTD_startQatDevice", "QZSTD_stopQatDevice", "QZSTD_createSeqProdState",
     "QZSTD_freeSeqProdState", "qatSequenceProducer", "QZSTD_hintSource", "QZSTD_getStats", "QZSTD_generateSequences",
-    "QZSTD_setCoalescing", "b200sp_parse_blocks",
+    "QZSTD_setCoalescing", "b200sp_parse_blocks", "b200sp_stage_reserve", "b200sp_parse_staged",
     "b200sp_driver_device_count", "b200sp_device_count", "b200sp_warmup", "b200sp_engine_create", "b200sp_engine_destroy",
     "b200sp_engine_device", "b200sp_engine_sm_count", "b200sp_parse_device", "b200sp_sync",
     "b200sp_parse_host", "b200sp_expand", "b200sp_verify_device", "b200sp_error_string", "b200sp_version",

@@ -180,6 +180,7 @@ struct b200sp_engine {
     unsigned long long *d_offsets; size_t d_offsetsCap;
     unsigned long long *d_packed; size_t d_packedCap;   // entries
     uint8_t *h_stage;    size_t h_stageCap;     // pinned staging for pageable inputs
+    uint32_t stageSlots;                        // slots reserved by b200sp_stage_reserve (scattered-block path)
     uint32_t *h_counts;  size_t h_countsCap;
     unsigned long long *h_offsets; size_t h_offsetsCap;  // chunk-local (pinned)
     unsigned long long *h_goffsets; size_t h_goffsetsCap; // global, handed to the caller
@@ -517,27 +518,50 @@ int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint3
     return B200SP_OK;
 }
 
-int b200sp_parse_blocks(b200sp_engine *e, const void *const *h_blocks, const uint32_t *sizes, uint32_t nBlocks,
-                        int level, b200sp_result *res)
+// Staging layout of the scattered-block path: [sizes (u32 per slot, padded to 16 B)] [slot 0] [slot 1] ... at a
+// 128 KiB stride, in pinned host memory and mirrored on the device.
+static size_t staged_sizes_bytes(uint32_t nSlots)
+{
+    return (static_cast<size_t>(nSlots) * sizeof(uint32_t) + 15u) & ~static_cast<size_t>(15);
+}
+
+int b200sp_stage_reserve(b200sp_engine *e, uint32_t nSlots, void **slots)
+{
+    if (!e || !slots || nSlots == 0) return fail(B200SP_EINVAL, "stage_reserve: bad argument");
+    CU_TRY(cudaSetDevice(e->device), "cudaSetDevice");
+    // the slot area starts at the offset the LARGEST reservation needs, so it never moves when fewer slots are used
+    if (nSlots > e->stageSlots) {
+        CU_TRY(cudaStreamSynchronize(e->stream), "sync before growing the staging area");
+        CU_TRY(grow_host(e->h_stage, e->h_stageCap, staged_sizes_bytes(nSlots) + static_cast<size_t>(nSlots) * B200SP_BLOCK_MAX),
+               "cudaMallocHost(stage)");
+        e->stageSlots = nSlots;
+    }
+    *slots = e->h_stage + staged_sizes_bytes(e->stageSlots);
+    return B200SP_OK;
+}
+
+int b200sp_parse_staged(b200sp_engine *e, const uint32_t *sizes, uint32_t nBlocks, int level, b200sp_result *res)
 {
     if (!e || !res) return fail(B200SP_EINVAL, "null engine/result");
     memset(res, 0, sizeof *res);
     if (level < 1 || level > 12) return fail(B200SP_EINVAL, "compression level outside 1..12");
     if (nBlocks == 0) return B200SP_OK;
-    if (!h_blocks || !sizes) return fail(B200SP_EINVAL, "null block list");
-    for (uint32_t b = 0; b < nBlocks; b++)
-        if (!h_blocks[b] || sizes[b] == 0 || sizes[b] > B200SP_BLOCK_MAX) return fail(B200SP_EINVAL, "block size must be 1..131072");
+    if (!sizes || nBlocks > e->stageSlots) return fail(B200SP_EINVAL, "parse_staged: more blocks than reserved slots");
+    bool allFull = true;
+    for (uint32_t b = 0; b < nBlocks; b++) {
+        if (sizes[b] == 0 || sizes[b] > B200SP_BLOCK_MAX) return fail(B200SP_EINVAL, "block size must be 1..131072");
+        allFull = allFull && sizes[b] == B200SP_BLOCK_MAX;
+    }
     CU_TRY(cudaSetDevice(e->device), "cudaSetDevice");
 
     const uint64_t stride = B200SP_BLOCK_MAX;
     const size_t seqStride = B200SP_SEQ_STRIDE, perBlockWorst = B200SP_BLOCK_MAX / 4 + 2;
-    const size_t sizesBytes = (static_cast<size_t>(nBlocks) * sizeof(uint32_t) + 15u) & ~static_cast<size_t>(15);
-    CU_TRY(grow_dev(e->d_src, e->d_srcCap, nBlocks * stride + sizesBytes + 16), "cudaMalloc(src)");
+    const size_t sizesBytes = staged_sizes_bytes(e->stageSlots);
+    CU_TRY(grow_dev(e->d_src, e->d_srcCap, sizesBytes + static_cast<size_t>(e->stageSlots) * stride + 16), "cudaMalloc(src)");
     CU_TRY(grow_dev(e->d_seqs, e->d_seqsCap, nBlocks * seqStride), "cudaMalloc(seqs)");
     CU_TRY(grow_dev(e->d_counts, e->d_countsCap, nBlocks), "cudaMalloc(counts)");
     CU_TRY(grow_dev(e->d_offsets, e->d_offsetsCap, nBlocks + kMaxChunks), "cudaMalloc(offsets)");
     CU_TRY(grow_dev(e->d_packed, e->d_packedCap, nBlocks * perBlockWorst), "cudaMalloc(packed)");
-    CU_TRY(grow_host(e->h_stage, e->h_stageCap, nBlocks * stride + sizesBytes), "cudaMallocHost(stage)");
     CU_TRY(grow_host(e->h_counts, e->h_countsCap, nBlocks), "cudaMallocHost(counts)");
     CU_TRY(grow_host(e->h_offsets, e->h_offsetsCap, nBlocks + kMaxChunks), "cudaMallocHost(offsets)");
     if (e->h_goffsetsCap < nBlocks + 1) {
@@ -547,17 +571,17 @@ int b200sp_parse_blocks(b200sp_engine *e, const void *const *h_blocks, const uin
         e->h_goffsetsCap = nBlocks + 1 + nBlocks / 4;
     }
 
-    // gather: sizes first (so one copy moves both), then the blocks at a fixed stride; only the bytes of
-    // each block travel
     uint32_t *hSizes = reinterpret_cast<uint32_t *>(e->h_stage);
     uint8_t *hBlocks = e->h_stage + sizesBytes;
     uint8_t *dSizes = e->d_src, *dBlocks = e->d_src + sizesBytes;
     cudaStream_t st = e->stream;
     memcpy(hSizes, sizes, nBlocks * sizeof(uint32_t));
-    CU_TRY(cudaMemcpyAsync(dSizes, hSizes, nBlocks * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D sizes");
-    for (uint32_t b = 0; b < nBlocks; b++) {
-        memcpy(hBlocks + b * stride, h_blocks[b], sizes[b]);
-        CU_TRY(cudaMemcpyAsync(dBlocks + b * stride, hBlocks + b * stride, sizes[b], cudaMemcpyHostToDevice, st), "H2D block");
+    if (allFull) {          // sizes and blocks are contiguous: one copy
+        CU_TRY(cudaMemcpyAsync(dSizes, hSizes, sizesBytes + static_cast<size_t>(nBlocks) * stride, cudaMemcpyHostToDevice, st), "H2D batch");
+    } else {                // only the bytes of each block travel
+        CU_TRY(cudaMemcpyAsync(dSizes, hSizes, nBlocks * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D sizes");
+        for (uint32_t b = 0; b < nBlocks; b++)
+            CU_TRY(cudaMemcpyAsync(dBlocks + b * stride, hBlocks + b * stride, sizes[b], cudaMemcpyHostToDevice, st), "H2D block");
     }
     int rc = launch_batch(e, dBlocks, static_cast<uint64_t>(nBlocks) * stride, B200SP_BLOCK_MAX, stride,
                           reinterpret_cast<const uint32_t *>(dSizes), nBlocks, level,
@@ -581,6 +605,23 @@ int b200sp_parse_blocks(b200sp_engine *e, const void *const *h_blocks, const uin
     res->offsets = reinterpret_cast<const uint64_t *>(e->h_goffsets);
     res->packed = reinterpret_cast<const uint64_t *>(e->h_packed);
     return B200SP_OK;
+}
+
+int b200sp_parse_blocks(b200sp_engine *e, const void *const *h_blocks, const uint32_t *sizes, uint32_t nBlocks,
+                        int level, b200sp_result *res)
+{
+    if (!e || !res) return fail(B200SP_EINVAL, "null engine/result");
+    memset(res, 0, sizeof *res);
+    if (nBlocks == 0) return B200SP_OK;
+    if (!h_blocks || !sizes) return fail(B200SP_EINVAL, "null block list");
+    for (uint32_t b = 0; b < nBlocks; b++)
+        if (!h_blocks[b] || sizes[b] == 0 || sizes[b] > B200SP_BLOCK_MAX) return fail(B200SP_EINVAL, "block size must be 1..131072");
+    void *slots = nullptr;
+    int rc = b200sp_stage_reserve(e, nBlocks, &slots);
+    if (rc) return rc;
+    for (uint32_t b = 0; b < nBlocks; b++)      // gather (callers that can copy in parallel use the two calls above directly)
+        memcpy(static_cast<uint8_t *>(slots) + static_cast<size_t>(b) * B200SP_BLOCK_MAX, h_blocks[b], sizes[b]);
+    return b200sp_parse_staged(e, sizes, nBlocks, level, res);
 }
 
 void b200sp_expand(const uint64_t *packed, size_t count, b200sp_sequence *out)

@@ -155,88 +155,102 @@ static size_t producer_error(QZSTD_State_T *s)
     return ZSTD_SEQUENCE_PRODUCER_ERROR;
 }
 
-/* ---- cross-thread coalescing: a dispatcher parses the pending single-block calls of all threads in one batch ---- */
-#define COALESCE_MAX_BATCH 1024
+/* ---- cross-thread coalescing: a dispatcher parses the pending single-block calls of all threads in one batch ----
+ *
+ * Two batch buffers (two engines with their own pinned staging and result arrays).  Requesters take a slot in the
+ * OPEN batch, copy their block into its staging slot themselves, and wait; the dispatcher closes the open batch
+ * (requests arriving from then on go to the other one), waits for the copies in flight, parses the batch on the GPU,
+ * and hands every requester a pointer to its packed entries, which the requester expands itself.  A buffer is
+ * reused once all its requesters have expanded.  The copies in, the expansions out and the GPU work of
+ * consecutive batches overlap; the dispatcher only launches and waits. */
+#define COALESCE_MAX_BATCH 296        /* two waves of one-block CTAs */
 
 typedef struct QZSTD_Request {
-    const void *src;
     uint32_t size;
-    int level;
-    ZSTD_Sequence *out;
-    size_t cap;
-    size_t rc;                      /* result: count or ZSTD_SEQUENCE_PRODUCER_ERROR */
     int done;
-    struct QZSTD_Request *next;
+    int ok;
+    size_t count;                   /* entries of this block */
+    const uint64_t *packed;         /* its entries in the batch's result array (valid until the requester consumed them) */
 } QZSTD_Request;
+
+typedef struct {
+    b200sp_engine *engine;
+    unsigned char *slots;           /* pinned staging, slot k at k * 128 KiB */
+    QZSTD_Request *reqs[COALESCE_MAX_BATCH];
+    uint32_t sizes[COALESCE_MAX_BATCH];
+    uint32_t taken;                 /* slots handed out */
+    uint32_t copied;                /* requesters that have finished copying in */
+    uint32_t toConsume;             /* requesters that still have to expand the last result */
+    int level;
+} QZSTD_Batch;
 
 static struct {
     pthread_mutex_t mu;
-    pthread_cond_t wake;            /* dispatcher: work arrived or stop requested */
-    pthread_cond_t finished;        /* requesters: some batch finished (broadcast) */
-    QZSTD_Request *head, *tail;
+    pthread_cond_t wake;            /* dispatcher: work arrived, copies finished, results consumed, stop requested */
+    pthread_cond_t finished;        /* requesters: a batch finished or the open batch changed (broadcast) */
+    QZSTD_Batch batch[2];
+    int open;                       /* index of the batch that takes new requests */
     int enabled;                    /* requested by QZSTD_setCoalescing / QZSTD_COALESCE */
     int running;                    /* dispatcher thread alive */
     int stop;
     pthread_t thread;
     unsigned long long batches, blocks;
-} g_co = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, NULL, 0, 0, 0, 0, 0, 0 };
+} g_co = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {{0}}, 0, 0, 0, 0, 0, 0, 0 };
 
 static void *coalesce_main(void *arg)
 {
-    b200sp_engine *engine = NULL;
-    const void **ptrs = (const void **)malloc(COALESCE_MAX_BATCH * sizeof(void *));
-    uint32_t *sizes = (uint32_t *)malloc(COALESCE_MAX_BATCH * sizeof(uint32_t));
-    QZSTD_Request **reqs = (QZSTD_Request **)malloc(COALESCE_MAX_BATCH * sizeof(QZSTD_Request *));
-    int healthy = ptrs && sizes && reqs && b200sp_engine_create(0, &engine) == B200SP_OK;
+    int healthy = 1, i;
     (void)arg;
+    for (i = 0; i < 2; i++) {
+        void *slots = NULL;
+        QZSTD_Batch *b = &g_co.batch[i];
+        if (b200sp_engine_create(0, &b->engine) != B200SP_OK ||
+            b200sp_stage_reserve(b->engine, COALESCE_MAX_BATCH, &slots) != B200SP_OK) healthy = 0;
+        b->slots = (unsigned char *)slots;
+    }
     pthread_mutex_lock(&g_co.mu);
+    if (!healthy) {
+        QZSTD_LOG(1, "Coalescing dispatcher could not start: %s\n", b200sp_error_string());
+        g_co.stop = 1;
+    }
+    g_co.running = healthy ? 2 : 1;             /* 2: accepting requests */
+    pthread_cond_broadcast(&g_co.finished);
     for (;;) {
-        uint32_t n = 0, i;
-        int level;
+        QZSTD_Batch *b;
         b200sp_result res;
+        uint32_t n, k;
         int ok;
-        while (!g_co.head && !g_co.stop) pthread_cond_wait(&g_co.wake, &g_co.mu);
-        if (!g_co.head && g_co.stop) break;
-        /* take the pending requests of the head's level, in arrival order */
-        level = g_co.head->level;
-        {
-            QZSTD_Request **link = &g_co.head, *t;
-            while (*link && n < COALESCE_MAX_BATCH) {
-                QZSTD_Request *r = *link;
-                if (r->level == level) { *link = r->next; reqs[n++] = r; }
-                else link = &r->next;
-            }
-            g_co.tail = NULL;                       /* requests of other levels (or beyond the batch limit) stay queued */
-            for (t = g_co.head; t; t = t->next) g_co.tail = t;
-        }
+        while (g_co.batch[g_co.open].taken == 0 && !g_co.stop) pthread_cond_wait(&g_co.wake, &g_co.mu);
+        if (g_co.batch[g_co.open].taken == 0 && g_co.stop) break;
+        /* the other buffer must be free before new requests may go there */
+        while (g_co.batch[g_co.open ^ 1].toConsume != 0) pthread_cond_wait(&g_co.wake, &g_co.mu);
+        b = &g_co.batch[g_co.open];
+        g_co.open ^= 1;                          /* close: later requests join the other batch */
+        g_co.batch[g_co.open].taken = 0;
+        g_co.batch[g_co.open].copied = 0;
+        pthread_cond_broadcast(&g_co.finished);  /* requesters waiting for room */
+        n = b->taken;
+        while (b->copied < n) pthread_cond_wait(&g_co.wake, &g_co.mu);
         pthread_mutex_unlock(&g_co.mu);
 
-        for (i = 0; i < n; i++) { ptrs[i] = reqs[i]->src; sizes[i] = reqs[i]->size; }
-        ok = healthy && b200sp_parse_blocks(engine, ptrs, sizes, n, level, &res) == B200SP_OK && res.nBlocks == n;
+        ok = healthy && b200sp_parse_staged(b->engine, b->sizes, n, b->level, &res) == B200SP_OK && res.nBlocks == n;
         if (!ok) QZSTD_LOG(1, "Coalesced parse failed: %s\n", b200sp_error_string());
-        for (i = 0; i < n; i++) {
-            QZSTD_Request *r = reqs[i];
-            size_t rc = ZSTD_SEQUENCE_PRODUCER_ERROR;
-            if (ok) {
-                rc = res.counts[i];
-                if (rc >= r->cap - 1) rc = ZSTD_SEQUENCE_PRODUCER_ERROR;        /* same guard as the reference (:1318-1322) */
-                else b200sp_expand(res.packed + res.offsets[i], rc, (b200sp_sequence *)r->out);
-            }
-            r->rc = rc;
-        }
+
         pthread_mutex_lock(&g_co.mu);
-        for (i = 0; i < n; i++) reqs[i]->done = 1;
+        for (k = 0; k < n; k++) {
+            QZSTD_Request *r = b->reqs[k];
+            r->ok = ok;
+            if (ok) { r->count = res.counts[k]; r->packed = res.packed + res.offsets[k]; }
+            r->done = 1;
+        }
+        b->toConsume = n;
         g_co.batches++; g_co.blocks += n;
         pthread_cond_broadcast(&g_co.finished);
     }
-    /* stop: whatever is still queued is refused */
-    while (g_co.head) { QZSTD_Request *r = g_co.head; g_co.head = r->next; r->rc = ZSTD_SEQUENCE_PRODUCER_ERROR; r->done = 1; }
-    g_co.tail = NULL;
     g_co.running = 0;
     pthread_cond_broadcast(&g_co.finished);
     pthread_mutex_unlock(&g_co.mu);
-    if (engine) b200sp_engine_destroy(engine);
-    free(ptrs); free(sizes); free(reqs);
+    for (i = 0; i < 2; i++) if (g_co.batch[i].engine) { b200sp_engine_destroy(g_co.batch[i].engine); g_co.batch[i].engine = NULL; }
     return NULL;
 }
 
@@ -246,7 +260,12 @@ static void coalesce_start_if_wanted(void)
     pthread_mutex_lock(&g_co.mu);
     if (g_co.enabled && !g_co.running && g_process.status == QZSTD_OK) {
         g_co.stop = 0;
-        if (pthread_create(&g_co.thread, NULL, coalesce_main, NULL) == 0) g_co.running = 1;
+        g_co.open = 0;
+        memset(g_co.batch, 0, sizeof g_co.batch);
+        if (pthread_create(&g_co.thread, NULL, coalesce_main, NULL) == 0) {
+            g_co.running = 1;
+            while (g_co.running == 1 && !g_co.stop) pthread_cond_wait(&g_co.finished, &g_co.mu);   /* engines ready */
+        }
     }
     pthread_mutex_unlock(&g_co.mu);
 }
@@ -256,7 +275,7 @@ static void coalesce_stop(void)
     pthread_t th;
     int join = 0;
     pthread_mutex_lock(&g_co.mu);
-    if (g_co.running) { g_co.stop = 1; th = g_co.thread; join = 1; pthread_cond_signal(&g_co.wake); }
+    if (g_co.running) { g_co.stop = 1; th = g_co.thread; join = 1; pthread_cond_broadcast(&g_co.wake); }
     pthread_mutex_unlock(&g_co.mu);
     if (join) pthread_join(th, NULL);
 }
@@ -265,16 +284,38 @@ static void coalesce_stop(void)
 static int coalesce_submit(const void *src, size_t srcSize, int level, ZSTD_Sequence *out, size_t cap, size_t *rc)
 {
     QZSTD_Request r;
+    QZSTD_Batch *b;
+    uint32_t k;
     pthread_mutex_lock(&g_co.mu);
-    if (!g_co.running || g_co.stop) { pthread_mutex_unlock(&g_co.mu); return -1; }
-    r.src = src; r.size = (uint32_t)srcSize; r.level = level; r.out = out; r.cap = cap;
-    r.rc = ZSTD_SEQUENCE_PRODUCER_ERROR; r.done = 0; r.next = NULL;
-    if (g_co.tail) g_co.tail->next = &r; else g_co.head = &r;
-    g_co.tail = &r;
+    for (;;) {
+        if (g_co.running != 2 || g_co.stop) { pthread_mutex_unlock(&g_co.mu); return -1; }
+        b = &g_co.batch[g_co.open];
+        if (b->taken < COALESCE_MAX_BATCH && (b->taken == 0 || b->level == level)) break;
+        pthread_cond_wait(&g_co.finished, &g_co.mu);        /* full, or another level: wait for the next batch */
+    }
+    k = b->taken++;
+    if (k == 0) b->level = level;
+    r.size = (uint32_t)srcSize; r.done = 0; r.ok = 0; r.count = 0; r.packed = NULL;
+    b->reqs[k] = &r;
+    b->sizes[k] = r.size;
+    pthread_mutex_unlock(&g_co.mu);
+
+    memcpy(b->slots + (size_t)k * B200SP_BLOCK_MAX, src, srcSize);          /* in parallel with the other requesters */
+
+    pthread_mutex_lock(&g_co.mu);
+    b->copied++;
     pthread_cond_signal(&g_co.wake);
     while (!r.done) pthread_cond_wait(&g_co.finished, &g_co.mu);
     pthread_mutex_unlock(&g_co.mu);
-    *rc = r.rc;
+
+    *rc = ZSTD_SEQUENCE_PRODUCER_ERROR;
+    if (r.ok && r.count < cap - 1) {            /* same guard as the reference (:1318-1322) */
+        b200sp_expand(r.packed, r.count, (b200sp_sequence *)out);
+        *rc = r.count;
+    }
+    pthread_mutex_lock(&g_co.mu);
+    if (--b->toConsume == 0) pthread_cond_signal(&g_co.wake);               /* the buffer may be reused */
+    pthread_mutex_unlock(&g_co.mu);
     return 0;
 }
 
