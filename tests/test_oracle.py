@@ -165,3 +165,30 @@ def test_lane_model_ragged_sizes(oracle, n):
         want = oracle.model_block(data, 3)
         got = oracle.lane_model_block(data, 3)
         assert got.shape == want.shape and (got == want).all()
+
+
+# ---- property test: random structured inputs (hypothesis) ----
+try:
+    from hypothesis import given, settings, strategies as st
+    HAVE_HYPOTHESIS = True
+except Exception:                                              # pragma: no cover
+    HAVE_HYPOTHESIS = False
+
+
+if HAVE_HYPOTHESIS:
+    _piece = st.one_of(
+        st.binary(min_size=1, max_size=40),                                          # literals
+        st.tuples(st.binary(min_size=1, max_size=12), st.integers(2, 60)).map(lambda t: t[0] * t[1]),   # periodic runs
+        st.integers(1, 600).map(lambda n: b"\x00" * n),                               # zero runs
+    )
+
+    @settings(max_examples=60, deadline=None)
+    @given(pieces=st.lists(_piece, min_size=1, max_size=60), repeat=st.integers(1, 3), level=st.sampled_from([1, 3, 6]))
+    def test_lane_model_property(oracle, pieces, repeat, level):
+        """Arbitrary mixtures of literals, periodic runs and zero runs, repeated so that far matches exist: the model's
+        sequences replay to the input and the lane-level formulation equals the serial one."""
+        data = (b"".join(pieces) * repeat)[:BLOCK]
+        want = oracle.model_block(data, level)
+        assert oracle.validate(data, want) == 0
+        got = oracle.lane_model_block(data, level)
+        assert got.shape == want.shape and (got == want).all()
