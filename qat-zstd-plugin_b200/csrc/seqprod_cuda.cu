@@ -41,8 +41,9 @@ bool device_usable(int dev)
 }
 
 // ---- wire format: offset | litLength << 17 | matchLength << 35 ----------------------------
-// The post-processing kernels of chunk k run while the parser CTAs of chunk k+1 own every SM (1024 threads
-// x 60 registers): they are sized (128 threads, <= 32 registers) to fit beside one parser CTA.
+// The post-processing kernels of chunk k are queued while the parser CTAs of chunk k+1 own every SM (a parser
+// CTA takes the whole register file): they are small and sit on a high-priority stream, so they get the first
+// SMs that free up.
 constexpr int kPostThreads = 128;
 
 __global__ void __launch_bounds__(32) scan_counts_kernel(const uint32_t *__restrict__ counts, uint32_t nBlocks,
