@@ -22,8 +22,8 @@ class Sequence(Structure):
 
 
 class ModelParams(Structure):
-    _fields_ = [("longBits", c_int), ("shortBits", c_int), ("shortBytes", c_int), ("minMatch", c_int),
-                ("extCap", c_int), ("lazyDepth", c_int), ("window", c_int)]
+    _fields_ = [("keyBytes", c_int), ("scan", c_int), ("minMatch", c_int), ("extCap", c_int),
+                ("lazyDepth", c_int), ("window", c_int), ("backExt", c_int)]
 
 
 def build() -> None:

@@ -5,8 +5,8 @@
  *   sw     : per-block ZSTD_generateSequences through the slot   (software seq-producer)
  *   model  : the serial model of the B200 match finder through the slot
  * and validates the model's sequences.  Model parameters can be overridden from the
- * environment (MODEL_LONGBITS, MODEL_SHORTBITS, MODEL_SHORTBYTES, MODEL_MINMATCH, MODEL_EXTCAP,
- * MODEL_LAZY, MODEL_WINDOW) for tuning experiments.
+ * environment (MODEL_KEYBYTES, MODEL_SCAN, MODEL_MINMATCH, MODEL_EXTCAP, MODEL_LAZY, MODEL_WINDOW,
+ * MODEL_BACKEXT) for tuning experiments.
  *
  * usage: ratio_probe <file> [level=3] [chunk=131072]
  */
@@ -63,16 +63,16 @@ int main(int argc, char **argv)
 
     ModelState ms; memset(&ms, 0, sizeof ms);
     seqmodel_params_for_level(level, &ms.prm);
-    env_int("MODEL_LONGBITS", &ms.prm.longBits);   env_int("MODEL_SHORTBITS", &ms.prm.shortBits);
-    env_int("MODEL_SHORTBYTES", &ms.prm.shortBytes); env_int("MODEL_MINMATCH", &ms.prm.minMatch);
-    env_int("MODEL_EXTCAP", &ms.prm.extCap);       env_int("MODEL_LAZY", &ms.prm.lazyDepth);
-    env_int("MODEL_WINDOW", &ms.prm.window);
+    env_int("MODEL_KEYBYTES", &ms.prm.keyBytes);   env_int("MODEL_SCAN", &ms.prm.scan);
+    env_int("MODEL_MINMATCH", &ms.prm.minMatch);   env_int("MODEL_EXTCAP", &ms.prm.extCap);
+    env_int("MODEL_LAZY", &ms.prm.lazyDepth);      env_int("MODEL_WINDOW", &ms.prm.window);
+    env_int("MODEL_BACKEXT", &ms.prm.backExt);
     for (int e = 1; e >= 0; e--) {
         ms.nseq = ms.nblocks = ms.bad = 0; ms.secs = 0;
         size_t c = oracle_compress_with_producer(src, sz, chunk, level, model_producer, &ms,
                                                  e ? ZSTD_ps_enable : ZSTD_ps_auto, 0, 1, &calls, &errs, &ok);
-        printf("   model(E%d) L%d/S%d(%dB) min%d cap%d lazy%d: %zu (%+.2f%% vs ref)  rt=%d errs=%zu bad=%zu  seq/blk=%.0f  B/seq=%.1f  model %.0f MB/s\n",
-               e, ms.prm.longBits, ms.prm.shortBits, ms.prm.shortBytes, ms.prm.minMatch, ms.prm.extCap,
+        printf("   model(E%d) key%dB scan%d backext%d min%d cap%d lazy%d: %zu (%+.2f%% vs ref)  rt=%d errs=%zu bad=%zu  seq/blk=%.0f  B/seq=%.1f  model %.0f MB/s\n",
+               e, ms.prm.keyBytes, ms.prm.scan, ms.prm.backExt, ms.prm.minMatch, ms.prm.extCap,
                ms.prm.lazyDepth, c, 100.0 * ((double)c / ref - 1), ok, errs, ms.bad,
                ms.nblocks ? (double)ms.nseq / ms.nblocks : 0.0, ms.nseq ? (double)sz / ms.nseq : 0.0,
                sz / ms.secs / 1e6);

@@ -2,15 +2,19 @@
  * seqmodel.c — serial CPU statement of the B200 match finder (see seqmodel.h).
  * TEST INFRASTRUCTURE ONLY: never linked into the product.
  *
- * The four steps below are what the sm_100a pipeline computes per 128 KiB block; the kernel
- * distributes them over warp roles (hash warps, two table warps, extension warps, one parse
- * warp) but must produce exactly this output.
+ * The steps below are what the sm_100a pipeline computes per 128 KiB block; the kernel
+ * distributes them over warp roles (hash/extension pool, one counting warp, parse and emit
+ * warps) but must produce exactly this output.
  *
- *   1. candidates  every position p <= n-8 hashes 8 bytes (long) and shortBytes bytes (short)
- *                  and reads-then-overwrites one slot of each table: the candidate is the most
- *                  recent earlier position with the same hash.
- *   2. extension   common prefix of src[p..] and src[cand..]: candidates are ranked on their first
- *                  16 bytes, the winner is extended up to extCap (and never past n).
+ *   1. candidates  every position p <= n-8 hashes keyBytes bytes into a 13-bit bucket and a 15-bit tag and is
+ *                  appended to its bucket's list (a stable counting sort of the positions by bucket: the
+ *                  "GPU-resident hash-chain table" - every bucket is the chain of ALL earlier positions with
+ *                  that hash, most recent last).  The candidates of p are the `scan` entries before it in
+ *                  its bucket whose tag equals its own, most recent first: the level-scaled search depth.
+ *   2. extension   every candidate is measured in full (common prefix of src[p..] and src[cand..], up to
+ *                  extCap and never past n); the longest wins, the nearer one on ties.  Then a position
+ *                  adopts its right neighbour's match when that match also holds one byte earlier
+ *                  (zstd's "catch up" by one; never across a 32-position group).
  *   3. propagation B(p) = the match, among all starting at q <= p, that reaches farthest right.
  *   4. parse       greedy left-to-right over B with lazy look-ahead; zero-literal sequences
  *                  repeating the previous offset are merged into their predecessor; the last
@@ -22,27 +26,12 @@
 #include <string.h>
 
 #define MODEL_MAX_BLOCK (1u << 17)
-#define MODEL_PROBE     16u          /* bytes compared per candidate before a winner is picked */
 
 static inline uint32_t rd32(const uint8_t *p)
 {
     uint32_t v;
     memcpy(&v, p, 4);
     return v;                       /* little-endian hosts only (x86-64, like the GPU) */
-}
-
-static inline uint32_t hash_long(uint32_t lo, uint32_t hi, int bits)
-{
-    return (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> (32 - bits);
-}
-
-static inline uint32_t hash_short(uint32_t lo, uint32_t hi, int bytes, int bits)
-{
-    uint32_t h;
-    if (bytes <= 4)      h = lo * 0x9E3779B1u;
-    else if (bytes == 5) h = lo * 0x9E3779B1u + (hi & 0xFFu) * 0xC2B2AE3Du;
-    else                 h = lo * 0x9E3779B1u + (hi & 0xFFFFu) * 0xC2B2AE3Du;
-    return h >> (32 - bits);
 }
 
 static inline uint32_t floorlog2(uint32_t v)   /* v >= 1 */
@@ -52,23 +41,18 @@ static inline uint32_t floorlog2(uint32_t v)   /* v >= 1 */
 
 void seqmodel_params_for_level(int level, SeqModelParams *prm)
 {
-    /* One parameter class per zstd strategy class. */
-    prm->longBits = 14;
-    prm->shortBits = 12;         /* 8 KiB: the kernel spends its shared memory on a wider pipeline window instead */
-    prm->shortBytes = 5;
+    /* One parameter class per zstd strategy class; the scan width is the level-scaled
+     * search depth (the reference hands the level to its engine, /root/reference/src/qatseqprod.c:1154). */
+    static const int scanOf[13] = { 0, 4, 4, 4, 4, 32, 32, 64, 64, 128, 128, 256, 256 };
+    if (level < 1) level = 1;
+    if (level > 12) level = 12;
+    prm->keyBytes = level <= 4 ? 5 : 4;
+    prm->scan = scanOf[level];
     prm->minMatch = 4;
     prm->extCap = 256;
-    prm->lazyDepth = 1;
+    prm->lazyDepth = level <= 4 ? 1 : 2;
     prm->window = 32;            /* lazy look-ahead stays inside the 32-position group one warp owns */
-    if (level <= 2) {            /* fast class */
-        prm->shortBytes = 6;
-        prm->lazyDepth = 0;
-    } else if (level <= 4) {     /* dfast class */
-        prm->lazyDepth = 1;
-    } else {                     /* greedy / lazy / lazy2 / btlazy2 classes */
-        prm->shortBytes = 4;
-        prm->lazyDepth = 2;
-    }
+    prm->backExt = 1;
 }
 
 typedef struct { uint32_t end, off; } BestMatch;   /* end = p + len (0 = none) */
@@ -78,61 +62,69 @@ static inline int32_t gain_of(uint32_t len, uint32_t off)
     return (int32_t)(len * 4u) - (int32_t)floorlog2(off + 1u);
 }
 
+static inline uint32_t key_hash(uint32_t lo, uint32_t hi, int keyBytes)
+{
+    const uint32_t mask = keyBytes <= 4 ? 0u : keyBytes == 5 ? 0xFFu : 0xFFFFu;
+    return lo * 0x9E3779B1u + (hi & mask) * 0xC2B2AE3Du;
+}
+
 /* Steps 1-2 for every position: own best match (len 0 = none).  Shared by seqmodel_block and by the
  * lane-level statement of the parse warps (lanemodel.c). */
 int seqmodel_own_matches(const uint8_t *src, size_t n, const SeqModelParams *prm, uint32_t *ownLen, uint32_t *ownOff)
 {
     const uint32_t N = (uint32_t)n;
     const uint32_t nh = N >= 8 ? N - 7 : 0;      /* positions that can hash 8 bytes */
-    const size_t szL = (size_t)1 << prm->longBits, szS = (size_t)1 << prm->shortBits;
-    uint16_t *tabL = (uint16_t *)malloc(szL * sizeof(uint16_t));
-    uint16_t *tabS = (uint16_t *)malloc(szS * sizeof(uint16_t));
-    if (!tabL || !tabS) { free(tabL); free(tabS); return -1; }
-    /* A slot keeps (position >> 1) of the most recent position with that hash: 16 bits cover the
-     * whole 128 KiB block.  The dropped parity bit is recovered by testing both 2v and 2v+1.
-     * 0xFFFF (positions 131070/131071, never hashable) is the empty marker. */
-    memset(tabL, 0xFF, szL * sizeof(uint16_t));
-    memset(tabS, 0xFF, szS * sizeof(uint16_t));
+    const uint32_t nB = 1u << SEQMODEL_BUCKET_BITS;
+    /* counting sort of the hashable positions by bucket: hist -> segment starts -> entries {pos | tag << 17} */
+    uint32_t *start = (uint32_t *)calloc(nB + 1, sizeof(uint32_t));
+    uint32_t *count = (uint32_t *)calloc(nB, sizeof(uint32_t));
+    uint32_t *sorted = (uint32_t *)malloc(((size_t)nh + 1) * sizeof(uint32_t));
+    if (!start || !count || !sorted) { free(start); free(count); free(sorted); return -1; }
+    for (uint32_t p = 0; p < nh; p++) {
+        const uint32_t v = key_hash(rd32(src + p), rd32(src + p + 4), prm->keyBytes);
+        const uint32_t b = v >> (32 - SEQMODEL_BUCKET_BITS);
+        if (start[b + 1] < SEQMODEL_BUCKET_CAP) start[b + 1]++;
+    }
+    for (uint32_t b = 0; b < nB; b++) start[b + 1] += start[b];
+    const uint32_t scan = (uint32_t)prm->scan < SEQMODEL_IDX_CAP ? (uint32_t)prm->scan : SEQMODEL_IDX_CAP;
     for (uint32_t p = 0; p < N; p++) {
         uint32_t bestLen = 0, bestOff = 0;
         if (p < nh) {
             const uint32_t lo = rd32(src + p), hi = rd32(src + p + 4);
-            const uint32_t hL = hash_long(lo, hi, prm->longBits);
-            const uint32_t hS = hash_short(lo, hi, prm->shortBytes, prm->shortBits);
-            const uint32_t base[2] = { 2u * tabL[hL], 2u * tabS[hS] };
-            tabL[hL] = (uint16_t)(p >> 1);
-            tabS[hS] = (uint16_t)(p >> 1);
+            const uint32_t v = key_hash(lo, hi, prm->keyBytes);
+            const uint32_t b = v >> (32 - SEQMODEL_BUCKET_BITS);
+            const uint32_t tag = (v >> (32 - SEQMODEL_BUCKET_BITS - SEQMODEL_TAG_BITS)) & ((1u << SEQMODEL_TAG_BITS) - 1u);
+            const uint32_t idx = count[b];                   /* entries of the bucket before p */
+            if (idx < SEQMODEL_BUCKET_CAP) { sorted[start[b] + idx] = p | (tag << 17); count[b] = idx + 1; }
             uint32_t lim = N - p;
             if (lim > (uint32_t)prm->extCap) lim = (uint32_t)prm->extCap;
-            /* Phase 1: each table contributes ONE candidate: of the two positions its slot stands
-             * for (2v, 2v+1) the one whose first 4 bytes equal ours, the nearer one if both do.  It is
-             * measured over its first PROBE bytes only.  The short-table candidate replaces the
-             * long-table one if it is longer, or as long and nearer.
-             * Phase 2: only the winner is extended, up to extCap. */
-            const uint32_t probe = lim < MODEL_PROBE ? lim : MODEL_PROBE;
-            const uint32_t a4 = rd32(src + p);
-            for (int t = 0; t < 2; t++) {
-                const uint32_t q0 = base[t];
-                uint32_t q = UINT32_MAX;
-                if (q0 < p && rd32(src + q0) == a4) q = q0;
-                if (q0 + 1 < p && rd32(src + q0 + 1) == a4) q = q0 + 1;
-                if (q == UINT32_MAX) continue;
-                const uint8_t *a = src + p, *b = src + q;
-                uint32_t ml = 4;
-                while (ml < probe && a[ml] == b[ml]) ml++;
-                const uint32_t off = p - q;
-                if (ml > bestLen || (ml == bestLen && off < bestOff)) { bestLen = ml; bestOff = off; }
-            }
-            if (bestLen == MODEL_PROBE) {
-                const uint8_t *a = src + p, *b = src + p - bestOff;
-                while (bestLen < lim && a[bestLen] == b[bestLen]) bestLen++;
+            const uint32_t avail = idx < scan ? idx : scan;
+            for (uint32_t j = 1; j <= avail; j++) {
+                const uint32_t e = sorted[start[b] + idx - j];
+                if ((e >> 17) != tag) continue;
+                const uint32_t q = e & 0x1FFFFu;
+                const uint8_t *a = src + p, *c = src + q;
+                uint32_t ml = 0;
+                while (ml < lim && a[ml] == c[ml]) ml++;
+                if (ml > bestLen) { bestLen = ml; bestOff = p - q; }      /* ties keep the nearer candidate */
             }
             if (bestLen < (uint32_t)prm->minMatch) bestLen = 0;
         }
         ownLen[p] = bestLen;
-        ownOff[p] = bestOff;
+        ownOff[p] = bestLen ? bestOff : 0;
     }
-    free(tabL); free(tabS);
+    free(start); free(count); free(sorted);
+    if (prm->backExt) {
+        /* ascending: own[p + 1] is still the searched value when p looks at it */
+        for (uint32_t p = 0; p + 1 < N; p++) {
+            if ((p & 31u) == 31u) continue;                  /* the neighbour belongs to another group (another warp) */
+            const uint32_t l1 = ownLen[p + 1], o1 = ownOff[p + 1];
+            if (l1 && p >= o1 && src[p] == src[p - o1] && l1 + 1 > ownLen[p] && l1 + 1 <= (uint32_t)prm->extCap) {
+                ownLen[p] = l1 + 1;
+                ownOff[p] = o1;
+            }
+        }
+    }
     return 0;
 }
 

@@ -26,14 +26,19 @@
 extern "C" {
 #endif
 
+#define SEQMODEL_BUCKET_BITS 13      /* buckets of the counting sort (key hash, top bits)                 */
+#define SEQMODEL_TAG_BITS    15      /* further hash bits kept with every entry to filter candidates      */
+#define SEQMODEL_BUCKET_CAP  65535u  /* entries a bucket can hold (16-bit counters); later positions search but are not inserted */
+#define SEQMODEL_IDX_CAP     16383u  /* the insertion index travels in 14 bits: scan <= this                */
+
 typedef struct {
-    int longBits;     /* log2 entries of the 8-byte-hash table                      */
-    int shortBits;    /* log2 entries of the short-hash table                       */
-    int shortBytes;   /* bytes hashed by the short hash: 4, 5 or 6                  */
-    int minMatch;     /* shortest match the parser may emit (>= 3)                  */
-    int extCap;       /* per-position extension cap in bytes (multiple of 4)        */
-    int lazyDepth;    /* 0 greedy, 1 lazy, 2 lazy2                                  */
-    int window;       /* lazy look-ahead never crosses a multiple of it (32 = one warp's group)   */
+    int keyBytes;     /* bytes hashed into the bucket key: 4, 5 or 6                                       */
+    int scan;         /* bucket entries examined per position, most recent first (the level-scaled depth)  */
+    int minMatch;     /* shortest match the parser may emit (>= 3)                                         */
+    int extCap;       /* per-position match length cap in bytes (<= 256)                                   */
+    int lazyDepth;    /* 0 greedy, 1 lazy, 2 lazy2                                                         */
+    int window;       /* lazy look-ahead never crosses a multiple of it (32 = one warp's group)            */
+    int backExt;      /* 1: a position adopts the match of the next position (same 32-group) when it also holds one byte earlier */
 } SeqModelParams;
 
 /* Parameters the kernels use for a zstd compression level (1..12). */
