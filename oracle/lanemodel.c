@@ -80,6 +80,10 @@ size_t lanemodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t 
                        const SeqModelParams *prm)
 {
     if (n > (1u << 17) || outCap == 0 || prm->window != (int)KGRP) return (size_t)-1;
+    if (seqmodel_incompressible(src, n, prm)) {          /* step 0 of the model: one literal run */
+        out[0].offset = 0; out[0].litLength = (uint32_t)n; out[0].matchLength = 0; out[0].rep = 0;
+        return 1;
+    }
     const uint32_t N = (uint32_t)n;
     const uint32_t nW = (N + KWIN - 1) / KWIN;
     const uint32_t nG = nW * KGPW;

@@ -43,7 +43,7 @@ void seqmodel_params_for_level(int level, SeqModelParams *prm)
 {
     /* One parameter class per zstd strategy class; the scan width is the level-scaled
      * search depth (the reference hands the level to its engine, /root/reference/src/qatseqprod.c:1154). */
-    static const int scanOf[13] = { 0, 4, 4, 4, 4, 32, 32, 64, 64, 128, 128, 256, 256 };
+    static const int scanOf[13] = { 0, 4, 4, 4, 8, 32, 64, 96, 96, 128, 128, 256, 256 };
     if (level < 1) level = 1;
     if (level > 12) level = 12;
     prm->keyBytes = level <= 4 ? 5 : 4;
@@ -83,7 +83,7 @@ int seqmodel_own_matches(const uint8_t *src, size_t n, const SeqModelParams *prm
     for (uint32_t p = 0; p < nh; p++) {
         const uint32_t v = key_hash(rd32(src + p), rd32(src + p + 4), prm->keyBytes);
         const uint32_t b = v >> (32 - SEQMODEL_BUCKET_BITS);
-        if (start[b + 1] < SEQMODEL_BUCKET_CAP) start[b + 1]++;
+        start[b + 1]++;
     }
     for (uint32_t b = 0; b < nB; b++) start[b + 1] += start[b];
     const uint32_t scan = (uint32_t)prm->scan < SEQMODEL_IDX_CAP ? (uint32_t)prm->scan : SEQMODEL_IDX_CAP;
@@ -95,7 +95,8 @@ int seqmodel_own_matches(const uint8_t *src, size_t n, const SeqModelParams *prm
             const uint32_t b = v >> (32 - SEQMODEL_BUCKET_BITS);
             const uint32_t tag = (v >> (32 - SEQMODEL_BUCKET_BITS - SEQMODEL_TAG_BITS)) & ((1u << SEQMODEL_TAG_BITS) - 1u);
             const uint32_t idx = count[b];                   /* entries of the bucket before p */
-            if (idx < SEQMODEL_BUCKET_CAP) { sorted[start[b] + idx] = p | (tag << 17); count[b] = idx + 1; }
+            sorted[start[b] + idx] = p | (tag << 17);
+            count[b] = idx + 1;
             uint32_t lim = N - p;
             if (lim > (uint32_t)prm->extCap) lim = (uint32_t)prm->extCap;
             const uint32_t avail = idx < scan ? idx : scan;
@@ -128,10 +129,49 @@ int seqmodel_own_matches(const uint8_t *src, size_t n, const SeqModelParams *prm
     return 0;
 }
 
+/* Step 0, the incompressible shortcut (/root/reference/src/qatseqprod.c:1308-1313 returns one literal run for a
+ * block the engine could not compress).  Every hashable position sets one bit of a SEQMODEL_BITMAP_BITS-bit map
+ * chosen by its key hash; hits = positions whose bit was already set.  A block whose hits stay below what chance
+ * alone produces (plus six standard deviations) holds too few repeated keys to be worth parsing. */
+static uint32_t isqrt32(uint32_t v)
+{
+    uint32_t r = 0;
+    for (uint32_t bit = 1u << 15; bit; bit >>= 1) { const uint32_t t = r | bit; if ((uint64_t)t * t <= v) r = t; }
+    return r;
+}
+
+uint32_t seqmodel_chance_threshold(uint32_t nh)
+{
+    const uint64_t M = SEQMODEL_BITMAP_BITS, x = nh;
+    const uint64_t a = x * x / M;                                   /* expected hits = M (x/M - 1 + exp(-x/M)), by its series */
+    const uint64_t e = a / 2 - a * x / (6 * M) + a * a / (24 * M);
+    return (uint32_t)e + 6u * isqrt32((uint32_t)e) + 24u;
+}
+
+int seqmodel_incompressible(const uint8_t *src, size_t n, const SeqModelParams *prm)
+{
+    const uint32_t N = (uint32_t)n, nh = N >= 8 ? N - 7 : 0;
+    uint8_t *seen = (uint8_t *)calloc(SEQMODEL_BITMAP_BITS, 1);
+    if (!seen) return 0;
+    uint32_t hits = 0;
+    for (uint32_t p = 0; p < nh; p++) {
+        const uint32_t v = key_hash(rd32(src + p), rd32(src + p + 4), prm->keyBytes);
+        const uint32_t i = (uint32_t)(((uint64_t)v * SEQMODEL_BITMAP_BITS) >> 32);
+        hits += seen[i];
+        seen[i] = 1;
+    }
+    free(seen);
+    return hits < seqmodel_chance_threshold(nh);
+}
+
 size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t outCap,
                       const SeqModelParams *prm)
 {
     if (n > MODEL_MAX_BLOCK || outCap == 0) return (size_t)-1;
+    if (seqmodel_incompressible(src, n, prm)) {
+        out[0].offset = 0; out[0].litLength = (uint32_t)n; out[0].matchLength = 0; out[0].rep = 0;
+        return 1;
+    }
 
     const uint32_t N = (uint32_t)n;
     uint32_t *ownLen = (uint32_t *)malloc((N + 1) * sizeof(uint32_t));

@@ -28,7 +28,7 @@ extern "C" {
 
 #define SEQMODEL_BUCKET_BITS 13      /* buckets of the counting sort (key hash, top bits)                 */
 #define SEQMODEL_TAG_BITS    15      /* further hash bits kept with every entry to filter candidates      */
-#define SEQMODEL_BUCKET_CAP  65535u  /* entries a bucket can hold (16-bit counters); later positions search but are not inserted */
+#define SEQMODEL_BITMAP_BITS 491520u /* bits of the repeated-key detector (60 KiB of shared memory)               */
 #define SEQMODEL_IDX_CAP     16383u  /* the insertion index travels in 14 bits: scan <= this                */
 
 typedef struct {
@@ -48,6 +48,10 @@ void   seqmodel_params_for_level(int level, SeqModelParams *prm);
  * tail), or (size_t)-1 if outCap is too small.  n <= 131072. */
 size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t outCap,
                       const SeqModelParams *prm);
+
+/* Step 0: 1 when the block holds no more repeated keys than chance produces; it is then emitted as one literal run. */
+int    seqmodel_incompressible(const uint8_t *src, size_t n, const SeqModelParams *prm);
+uint32_t seqmodel_chance_threshold(uint32_t nh);
 
 /* Steps 1-2 of the model for every position p: ownLen[p] (0 = no match >= minMatch) and ownOff[p].
  * Arrays hold n entries.  Returns 0, or -1 on allocation failure. */

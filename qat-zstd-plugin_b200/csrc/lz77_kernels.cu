@@ -4,21 +4,26 @@
  *
  * This is the B200 replacement for the QAT LZ4s engine + QZSTD_decLz4s
  * (/root/reference/src/qatseqprod.c:1245-1249 submit, :1013-1091 token walk, :1308-1313
- * incompressible shortcut).  Output convention is the reference's: matchLength >= 3 for real
- * matches, the last entry is {offset 0, trailing literals, matchLength 0}, `rep` is 0.
+ * incompressible shortcut, level handed to the engine at :1154).  Output convention is the reference's:
+ * matchLength >= 3 for real matches, the last entry is {offset 0, trailing literals, matchLength 0}, `rep` is 0.
  *
  * One persistent CTA per SM; a CTA owns one block at a time:
- *   - the block is staged into shared memory with 1-D TMA bulk copies (UBLKCP), 16 KiB per
- *     mbarrier so the pipeline starts before the whole block has landed;
- *   - both hash tables (16 Ki + 4 Ki x u16, positions stored >> 1) live in shared memory;
- *   - the block flows through rings of windows (52 groups of 32 positions), one role per stage time t:
- *       pool        26 warps    one queue of 52 fused tasks per stage (two per warp): task g probes both
- *                               candidates of group g of window t-2 on 16 bytes, extends long matches
- *                               warp-cooperatively and leaves the packed prefix maximum of match ends, and -
- *                               inside its probe block, hidden behind the candidate loads - hashes group g of
- *                               window t (8-byte + short hash, intra-warp duplicate links by MATCH.ANY)
- *       T  table    window t-1   2 warps  one warp per table walks the window in order: read slot,
- *                               overwrite with the newer position (exact serial semantics)
+ *   - the block is staged into shared memory with 1-D TMA bulk copies (UBLKCP);
+ *   - phase A (all warps): every position's key hash feeds a histogram of the 8192 key buckets and a 480 Kbit
+ *     repeated-key bitmap.  A block with no more repeated keys than chance produces is emitted as one literal run
+ *     (the incompressible shortcut).  Otherwise the histogram is scanned into bucket segment starts: the table is a
+ *     stable counting sort of the block's positions by bucket - every bucket is the chain of all earlier
+ *     positions with that hash, contiguous, most recent last - in this CTA's scratch in global memory (L2);
+ *   - the block then flows through rings of windows (52 groups of 32 positions), one role per stage time t:
+ *       pool        26 warps    one queue of 52 fused tasks per stage (two per warp): task g scans the last `scan`
+ *                               entries of each position's bucket for group g of window t-2 (16-byte loads of the
+ *                               sorted table, tag filter, most recent first; the longest match wins - `scan` is the
+ *                               level-scaled search depth), adopts the right neighbour's match when it also holds one
+ *                               byte earlier, leaves the packed prefix maximum of match ends, and - hidden behind its
+ *                               first loads - hashes group g of window t
+ *       T  table    window t-1   1 warp   walks the window in order: bucket counter += multiplicity (exact serial
+ *                               insertion index of every position), stores the position into its slot of the sorted
+ *                               table, hands slot and index to the pool
  *       P1 entries  window t-3   2 warps  (one per half window) lane = group: carry of the previous 8 groups,
  *                               lazy decisions memoised as link words, group entries iterated to the serial
  *                               fixed point; the entry of the second half is handed over through shared memory
@@ -147,10 +152,10 @@ __device__ __forceinline__ uint32_t ring_byte(uint32_t group, uint32_t lane)   /
 
 struct Shared {         // 32-bit shared-window addresses
     uint32_t in;        // the staged block (+ pad)
-    uint32_t tabL;      // u16[1 << kLongBits]
-    uint32_t tabS;      // u16[1 << kShortBits]
-    uint32_t ringH;     // u32[2][kWindow]      H -> T: per table {hash:14 | linked:1 | last:1}, long in the low half
-    uint32_t ringC;     // u32[kRingC][kWindow] candidates {long u16 | short u16} (H, T) -> packed prefix maxima (E)
+    uint32_t tab;       // u32[kBuckets]        phase A: histogram; then {segment start / 8 : 15 | entries so far : 17}
+    uint32_t bitmap;    // kBitmapBits bits     phase A only: overlays the spare table and the rings
+    uint32_t ringH;     // u32[2][kWindow]      H -> T: {valid:1 | bucket:13 | tag:15}
+    uint32_t ringC;     // u32[kRingC][kWindow] {slot in the sorted table:18 | insertion index (capped):14} (T) -> packed prefix maxima (E)
     uint32_t ringL;     // u32[2][kWindow]      P1 -> P2: memoised decisions {end:9 | take lane:5 | offset:17}
     uint32_t gmax;      // u32[kRingC][kGroups] packed farthest-reaching match of each group
     uint32_t gown;      // u32[kRingC][kGroups] lanes whose own prefix maximum is a usable match
@@ -164,24 +169,26 @@ struct Shared {         // 32-bit shared-window addresses
     uint32_t ecVal;     // emit warps: u32[3] anchor, previous offset, sequences written, after the publisher's half ...
     uint32_t ecTag;     // ... same numbering
     uint32_t emTag;     // emit warps: window + 1 once the first half's sequences are in memory
+    uint32_t hits;      // phase A: positions whose bitmap bit was already set
+    uint32_t scan;      // phase A: u32[32] warp totals of the segment scan (in the spare table)
 };
 
 // ------------------------------------------------------------------------------------------
-// H: hashes of one 32-position group.  Lanes whose hash already occurred earlier in the group get
-// their candidate here (the nearest such lane); the others are left to the table warps.
-//   ringH word, per table: {hash:14 | linked:1 | last:1}   (invalid lanes: linked, not last)
-//   ringC word: {long candidate u16 | short candidate u16 << 16}, 0xFFFF = none / to be filled by T
+// H: key hash of one 32-position group -> ringH word {valid:1 | bucket:13 | tag:15} (the top 28 bits of the hash).
 // ------------------------------------------------------------------------------------------
-template <int N>      // N groups per task, interleaved by hand: the MATCH.ANY latencies of all of them overlap
-__device__ __forceinline__ void stage_hash(const Shared &S, uint32_t w, const uint32_t (&group)[N], uint32_t lane,
-                                           uint32_t nh, uint32_t shortMask)
+__device__ __forceinline__ uint32_t key_hash(uint32_t lo, uint32_t hi, uint32_t keyMask)
 {
-    uint32_t p[N], hL[N], hS[N], w0[N], w1[N], w2[N];
-    bool valid[N];
+    return lo * 0x9E3779B1u + (hi & keyMask) * 0xC2B2AE3Du;
+}
+
+template <int N>      // N groups per task, interleaved by hand
+__device__ __forceinline__ void stage_hash(const Shared &S, uint32_t w, const uint32_t (&group)[N], uint32_t lane,
+                                           uint32_t nh, uint32_t keyMask)
+{
+    uint32_t p[N], w0[N], w1[N], w2[N];
 #pragma unroll
     for (int i = 0; i < N; i++) {
         p[i] = w * kWindow + group[i] * 32u + lane;
-        valid[i] = p[i] < nh;
         const uint32_t a = S.in + (min(p[i], kBlockMax) & ~3u);       // reads stay inside the padded buffer
         w0[i] = ldsc32(a); w1[i] = ldsc32(a + 4u); w2[i] = ldsc32(a + 8u);
     }
@@ -190,63 +197,51 @@ __device__ __forceinline__ void stage_hash(const Shared &S, uint32_t w, const ui
         const uint32_t sh = (p[i] & 3u) * 8u;
         const uint32_t lo = __funnelshift_r(w0[i], w1[i], sh);
         const uint32_t hi = __funnelshift_r(w1[i], w2[i], sh);
-        hL[i] = (lo * 0x9E3779B1u + hi * 0x85EBCA77u) >> (32 - kLongBits);
-        hS[i] = (lo * 0x9E3779B1u + (hi & shortMask) * 0xC2B2AE3Du) >> (32 - kShortBits);
-    }
-    uint32_t mL[N], mS[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) {    // invalid lanes get unique keys so they never link
-        mL[i] = __match_any_sync(0xFFFFFFFFu, valid[i] ? hL[i] : (0x10000u | lane));
-        mS[i] = __match_any_sync(0xFFFFFFFFu, valid[i] ? hS[i] : (0x10000u | lane));
-    }
-    const uint32_t ltMask = (1u << lane) - 1u;
-    const uint32_t geMask = ~((2u << lane) - 1u);      // lanes strictly above
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        const uint32_t bL = mL[i] & ltMask, bS = mS[i] & ltMask;
-        // nearest earlier lane with the same hash -> candidate position >> 1
-        const uint32_t cL = bL ? (p[i] - lane + (31u - __clz(bL))) >> 1 : 0xFFFFu;
-        const uint32_t cS = bS ? (p[i] - lane + (31u - __clz(bS))) >> 1 : 0xFFFFu;
-        const uint32_t linkedL = (bL != 0u) || !valid[i], linkedS = (bS != 0u) || !valid[i];
-        const uint32_t lastL = valid[i] && (mL[i] & geMask) == 0u, lastS = valid[i] && (mS[i] & geMask) == 0u;
-        const uint32_t vL = valid[i] ? hL[i] : 0u, vS = valid[i] ? hS[i] : 0u;
-        const uint32_t ri = ring_byte(group[i], lane);
-        sts32(S.ringH + (w & 1u) * (kWindow * 4u) + ri, (vL | (linkedL << 14) | (lastL << 15)) | ((vS | (linkedS << 14) | (lastS << 15)) << 16));
-        sts32(S.ringC + (w & (kRingC - 1)) * (kWindow * 4u) + ri, cL | (cS << 16));
+        const uint32_t v = key_hash(lo, hi, keyMask);
+        sts32(S.ringH + (w & 1u) * (kWindow * 4u) + ring_byte(group[i], lane), p[i] < nh ? (v >> 4) | (1u << 28) : 0u);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// T: one warp walks one table over a window, group by group, in position order, and fills the
-// candidates of the lanes H could not link inside their group.
+// T: one warp walks the window group by group, in position order.  A position's insertion index in its bucket is
+// the bucket's counter plus the number of earlier lanes of the group with the same bucket (MATCH.ANY); the last
+// such lane adds the multiplicity to the counter: exact serial semantics.  The position goes into its slot of the
+// sorted table (global scratch; read by the pool one stage later), slot and index go to the pool through ringC.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_table(const Shared &S, uint32_t tab, uint32_t half, uint32_t w, uint32_t lane)
+__device__ __forceinline__ void stage_table(const Shared &S, uint32_t w, uint32_t lane, uint32_t *sorted)
 {
     const uint32_t rh = S.ringH + (w & 1u) * (kWindow * 4u);
-    const uint32_t rc = S.ringC + (w & (kRingC - 1)) * (kWindow * 4u) + half * 2u;
-    const uint32_t windowBase = w * kWindow, sh = half * 16u;
+    const uint32_t rc = S.ringC + (w & (kRingC - 1)) * (kWindow * 4u);
+    const uint32_t windowBase = w * kWindow;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const uint32_t geMask = ~((2u << lane) - 1u);      // lanes strictly above
 #pragma unroll 1
-    for (uint32_t g0 = 0; g0 < kGroups; g0 += 8) {
-        uint32_t hw[8], tv[8];
+    for (uint32_t g0 = 0; g0 < kGroups; g0 += 4) {
+        uint32_t hw[4], m[4];
 #pragma unroll
-        for (int k = 0; k < 8; k++)      // groups past the window's end: linked, not last -> no table access below
-            hw[k] = g0 + k < kGroups ? (lds32(rh + ring_byte(g0 + k, lane)) >> sh) & 0xFFFFu : 0x4000u;
+        for (int k = 0; k < 4; k++)      // groups past the window's end: invalid
+            hw[k] = g0 + k < kGroups ? lds32(rh + ring_byte(g0 + k, lane)) : 0u;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint32_t ha = tab + (hw[k] & 0x3FFFu) * 2u;
-            const uint32_t p = windowBase + (g0 + k) * 32u + lane;
-            tv[k] = lds16(ha);
-            if (hw[k] & 0x8000u) sts16(ha, p >> 1);
+        for (int k = 0; k < 4; k++)      // invalid lanes get unique keys so they never pair up
+            m[k] = __match_any_sync(0xFFFFFFFFu, (hw[k] >> 28) ? (hw[k] >> 15) & (kBuckets - 1u) : (0x10000u | lane));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool valid = (hw[k] >> 28) != 0u;
+            const uint32_t ta = S.tab + ((hw[k] >> 15) & (kBuckets - 1u)) * 4u;
+            const uint32_t rank = __popc(m[k] & ltMask);
+            const uint32_t e = lds32(ta);
+            if (valid && (m[k] & geMask) == 0u) sts32(ta, e + rank + 1u);   // the 17-bit counter never carries into the start
             __syncwarp();       // orders this group's stores before the next group's loads
+            const uint32_t idx = (e & 0x1FFFFu) + rank;
+            const uint32_t slot = (e >> 17) * kSegAlign + idx;
+            if (valid) sorted[slot] = (windowBase + (g0 + k) * 32u + lane) | ((hw[k] & 0x7FFFu) << 17);
+            if (g0 + k < kGroups) sts32(rc + ring_byte(g0 + k, lane), valid ? (slot << 14) | min(idx, kIdxCap) : 0u);
         }
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (!(hw[k] & 0x4000u)) sts16(rc + ring_byte(g0 + k, lane), tv[k]);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// E: candidates of one group -> best match per position -> prefix-max of match ends
+// E: bucket scan of one group -> best match per position -> prefix-max of match ends
 // ringC out: packed prefix maximum {end - groupStart:9 | 31 - lane:6 | offset:17} (0 = none so far)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t first_diff_16(uint32_t x1, uint32_t x2, uint32_t x3)
@@ -260,21 +255,25 @@ __device__ __forceinline__ uint32_t first_diff_16(uint32_t x1, uint32_t x2, uint
     return len;
 }
 
+__device__ __forceinline__ uint4 ldg128_cg(const uint32_t *p)      // L2 only: the entries were stored by the table warp a stage ago
+{
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 template <bool kFuseHash>
 __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32_t group, uint32_t lane,
                                              uint32_t p, uint32_t n, uint32_t nh, uint32_t minMatch,
-                                             uint32_t extCap, uint32_t hashWindow = 0, uint32_t hashNh = 0,
-                                             uint32_t shortMask = 0)
+                                             uint32_t extCap, uint32_t scan, uint32_t keyMask, const uint32_t *sorted,
+                                             uint32_t hashWindow = 0, uint32_t hashNh = 0)
 {
-    const uint32_t slot = w & (kRingC - 1);
-    const uint32_t idx = S.ringC + slot * (kWindow * 4u) + ring_byte(group, lane);
+    const uint32_t slotC = w & (kRingC - 1);
+    const uint32_t idx = S.ringC + slotC * (kWindow * 4u) + ring_byte(group, lane);
     const uint32_t cw = ldsc32(idx);
-    const uint32_t cL = cw & 0xFFFFu, cS = cw >> 16;
     const uint32_t in = S.in;
     const bool valid = p < nh;
-    uint32_t bestLen = 0, bestOff = 0;
     const uint32_t lim = valid ? min(n - p, extCap) : 0u;
-    const uint32_t probe = min(lim, kProbe);
     // our own first 16 bytes, as four unaligned words (reads stay inside the padded buffer)
     uint32_t a0, a1, a2, a3;
     {
@@ -283,72 +282,76 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32
         a0 = __funnelshift_r(x0, x1, sh); a1 = __funnelshift_r(x1, x2, sh);
         a2 = __funnelshift_r(x2, x3, sh); a3 = __funnelshift_r(x3, x4, sh);
     }
-    // both candidates' first 20 bytes: the slot stands for positions 2c and 2c+1 (same 32-bit word row)
-    uint32_t yy[2][5];
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        const uint32_t a = in + (min(2u * (t ? cS : cL), kBlockMax) & ~3u);
-#pragma unroll
-        for (int k = 0; k < 5; k++) yy[t][k] = ldsc32(a + 4u * k);
-    }
-    if (kFuseHash) {        // same basic block as the probe: the MATCH.ANY latency hides behind the loads above
+    // the entries of our bucket before us: [s - avail, s), most recent last
+    const uint32_t s = cw >> 14;
+    const uint32_t avail = valid ? min(scan, cw & 0x3FFFu) : 0u;
+    const uint32_t first = s - avail;
+    int32_t A = avail ? static_cast<int32_t>((s - 1u) >> 2) : -1;        // 16-byte chunk of the table we read next
+    const int32_t Alast = avail ? static_cast<int32_t>(first >> 2) : 0;
+    uint4 chunk = make_uint4(0u, 0u, 0u, 0u);
+    if (A >= Alast) chunk = ldg128_cg(sorted + 4 * A);
+    if (kFuseHash) {        // same basic block as the first loads: their latency hides the hash
         const uint32_t gs[1] = {group};
-        stage_hash<1>(S, hashWindow, gs, lane, hashNh, shortMask);
+        stage_hash<1>(S, hashWindow, gs, lane, hashNh, keyMask);
     }
-#pragma unroll
-    for (int t = 0; t < 2; t++) {
-        const uint32_t c = t ? cS : cL;
-        // pick the one of 2c, 2c+1 whose first 4 bytes equal ours, the nearer one if both do.
-        // 0xFFFF (empty) fails q0 < p by construction.
-        const uint32_t q0 = 2u * c;
-        const uint32_t sh0 = (q0 & 3u) * 8u;   // q0 even: sh0 is 0 or 16
-        const uint32_t y0 = yy[t][0], y1 = yy[t][1], y2 = yy[t][2], y3 = yy[t][3], y4 = yy[t][4];
-        const bool c0 = valid && q0 < p && __funnelshift_r(y0, y1, sh0) == a0;
-        const bool c1 = valid && q0 + 1u < p && __funnelshift_r(y0, y1, sh0 + 8u) == a0;
-        const uint32_t sh = sh0 + (c1 ? 8u : 0u);
-        const uint32_t b1 = __funnelshift_r(y1, y2, sh), b2 = __funnelshift_r(y2, y3, sh), b3 = __funnelshift_r(y3, y4, sh);
-        uint32_t ml = min(first_diff_16(a1 ^ b1, a2 ^ b2, a3 ^ b3), probe);
-        const uint32_t off = p - q0 - (c1 ? 1u : 0u);
-        if (!(c0 || c1)) ml = 0;
-        if (ml > bestLen || (ml == bestLen && ml > 0 && off < bestOff)) { bestLen = ml; bestOff = off; }
-    }
-
-    // Long extension of winners that filled the probe.  A lane continuing its predecessor's
-    // match (same offset, both filled the probe) derives its length from the run head; heads are
-    // extended by the whole warp, 128 bytes per step, far enough to serve all their followers.
-    const bool job = (bestLen == kProbe) && (lim > kProbe);
-    const uint32_t prevOff = __shfl_up_sync(0xFFFFFFFFu, bestOff, 1);
-    const uint32_t jobs = __ballot_sync(0xFFFFFFFFu, job);
-    const bool follower = job && lane > 0 && ((jobs >> (lane - 1)) & 1u) && prevOff == bestOff;
-    uint32_t heads = jobs & ~__ballot_sync(0xFFFFFFFFu, follower);
-    const uint32_t myHead = job ? 31u - __clz(heads & ((2u << lane) - 1u)) : 32u;
-    while (heads) {
-        const uint32_t h = __ffs(heads) - 1;
-        heads &= heads - 1;
-        const uint32_t ph = p - lane + h;                               // head position (uniform)
-        const uint32_t offh = __shfl_sync(0xFFFFFFFFu, bestOff, h);
-        const uint32_t qh = ph - offh;
-        const uint32_t reach = min(n - ph, extCap + 32u);               // how far any follower may need
-        uint32_t U = reach;
-#pragma unroll 1
-        for (uint32_t k0 = kProbe; k0 < reach; k0 += 128u) {
-            const uint32_t k = k0 + lane * 4u;
-            uint32_t x = 0;
-            if (k < reach) x = ld32u(in, ph + k) ^ ld32u(in, qh + k);
-            const uint32_t bad = __ballot_sync(0xFFFFFFFFu, x != 0u);
-            if (bad) {
-                const uint32_t l = __ffs(bad) - 1;
-                const uint32_t xl = __shfl_sync(0xFFFFFFFFu, x, l);
-                U = min(reach, k0 + l * 4u + ((__ffs(xl) - 1) >> 3));
-                break;
+    const uint32_t tag = (key_hash(a0, a1, keyMask) >> 4) & 0x7FFFu;
+    uint32_t bestLen = 0, bestOff = 0;
+    while (__any_sync(0xFFFFFFFFu, A >= Alast)) {
+        uint32_t pend = 0;
+        const uint4 cur = chunk;
+        if (A >= Alast) {
+            const uint32_t i0 = 4u * static_cast<uint32_t>(A);
+            if ((cur.x >> 17) == tag && i0 >= first) pend |= 1u;                       // i0 < s always holds
+            if ((cur.y >> 17) == tag && i0 + 1u >= first && i0 + 1u < s) pend |= 2u;
+            if ((cur.z >> 17) == tag && i0 + 2u >= first && i0 + 2u < s) pend |= 4u;
+            if ((cur.w >> 17) == tag && i0 + 3u >= first && i0 + 3u < s) pend |= 8u;
+            A--;
+            if (A >= Alast) chunk = ldg128_cg(sorted + 4 * A);                          // in flight while we measure
+        }
+        while (__any_sync(0xFFFFFFFFu, pend != 0u)) {
+            if (pend) {
+                // most recent first; a later (farther) candidate must be strictly longer
+                const uint32_t j = 31u - __clz(pend);
+                pend ^= 1u << j;
+                const uint32_t e = j == 3u ? cur.w : j == 2u ? cur.z : j == 1u ? cur.y : cur.x;
+                const uint32_t q = e & 0x1FFFFu;
+                bool go = true;
+                if (bestLen >= kProbe) go = ld32u(in, p + bestLen - 3u) == ld32u(in, q + bestLen - 3u);   // cannot be longer otherwise
+                if (go) {
+                    const uint32_t qa = in + (q & ~3u), sh = (q & 3u) * 8u;
+                    const uint32_t y0 = ldsc32(qa), y1 = ldsc32(qa + 4u), y2 = ldsc32(qa + 8u), y3 = ldsc32(qa + 12u), y4 = ldsc32(qa + 16u);
+                    uint32_t ml = 0;
+                    if (__funnelshift_r(y0, y1, sh) == a0) {
+                        ml = first_diff_16(a1 ^ __funnelshift_r(y1, y2, sh), a2 ^ __funnelshift_r(y2, y3, sh), a3 ^ __funnelshift_r(y3, y4, sh));
+                        if (ml == kProbe) {
+                            uint32_t k = kProbe;
+                            while (k < lim) {
+                                const uint32_t x = ld32u(in, p + k) ^ ld32u(in, q + k);
+                                if (x) { k += (__ffs(x) - 1) >> 3; break; }
+                                k += 4u;
+                            }
+                            ml = k;
+                        }
+                        ml = min(ml, lim);
+                    }
+                    if (ml > bestLen) { bestLen = ml; bestOff = p - q; }
+                    if (bestLen >= lim) { pend = 0u; A = Alast - 1; }      // as long as a match can get: nothing farther can win
+                }
             }
         }
-        if (myHead == h) bestLen = min(lim, U - (lane - h));
+    }
+    if (bestLen < minMatch) { bestLen = 0; bestOff = 0; }
+    // zstd's "catch up" by one byte: adopt the right neighbour's match if it also holds one byte earlier
+    {
+        const uint32_t l1 = __shfl_down_sync(0xFFFFFFFFu, bestLen, 1), o1 = __shfl_down_sync(0xFFFFFFFFu, bestOff, 1);
+        const bool cand = lane < 31u && l1 != 0u && p >= o1 && l1 + 1u > bestLen && l1 + 1u <= extCap;
+        const uint32_t back = cand ? lds32(in + ((p - o1) & ~3u)) >> (((p - o1) & 3u) * 8u) : ~a0;
+        if (cand && ((back ^ a0) & 0xFFu) == 0u) { bestLen = l1 + 1u; bestOff = o1; }
     }
     // Pack {end relative to the group start (9 bits), 31 - lane (6 bits), offset (17 bits)}: an unsigned
     // max over packed words picks the farthest-reaching match and, on ties, the older one.
     uint32_t pk = 0;
-    if (bestLen >= minMatch) pk = ((lane + bestLen) << 23) | ((31u - lane) << 17) | bestOff;
+    if (bestLen) pk = ((lane + bestLen) << 23) | ((31u - lane) << 17) | bestOff;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pk, d);
@@ -356,7 +359,7 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32
     }
     sts32(idx, pk);                                      // prefix-max within the group
     const uint32_t own = __ballot_sync(0xFFFFFFFFu, (pk >> 23) >= lane + minMatch);
-    if (lane == 31) { sts32(S.gmax + (slot * 64u + group) * 4u, pk); sts32(S.gown + (slot * 64u + group) * 4u, own); }
+    if (lane == 31) { sts32(S.gmax + (slotC * 64u + group) * 4u, pk); sts32(S.gown + (slotC * 64u + group) * 4u, own); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -619,6 +622,18 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
 // ------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------
+// Hits that chance alone produces in the repeated-key bitmap for nh insertions, plus six standard deviations:
+// M (x - 1 + exp(-x)), x = nh / M, by its series in integer arithmetic (oracle/seqmodel.c:seqmodel_chance_threshold).
+__device__ __forceinline__ uint32_t chance_threshold(uint32_t nh)
+{
+    const unsigned long long M = kBitmapBits, x = nh;
+    const unsigned long long a = x * x / M;
+    const uint32_t e = static_cast<uint32_t>(a / 2 - a * x / (6 * M) + a * a / (24 * M));
+    uint32_t r = 0;
+    for (uint32_t bit = 1u << 15; bit; bit >>= 1) { const uint32_t t = r | bit; if (static_cast<unsigned long long>(t) * t <= e) r = t; }
+    return e + 6u * r + 24u;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParseParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -627,13 +642,13 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         uint32_t p;
         asm volatile("mov.u32 %0, %1;" : "=r"(p) : "r"(smem_u32(smem)));   // opaque: one register, never re-derived
         S.in = p;    p += kSmemInput;
-        S.tabL = p;  p += kSmemTabL;
-        S.tabS = p;  p += kSmemTabS;
+        S.tab = p;   p += kSmemTabL;
+        S.bitmap = p; p += kSmemTabS;          // the bitmap of phase A runs from here through the rings
         S.ringH = p; p += kSmemRingH;
         S.ringC = p; p += kSmemRingC;
         S.ringL = p; p += kSmemRingL;
-        S.gmax = p;  p += kRingC * 64 * 4;
-        S.gown = p;  p += kRingC * 64 * 4;
+        S.gmax = p;  S.scan = p; p += kRingC * 64 * 4;      // phase A borrows the group words (rewritten before they are read)
+        S.gown = p;  S.hits = p; p += kRingC * 64 * 4;
         S.hasA = p;  p += 2 * 64 * 4;
         S.entA = p;  p += 2 * 64 * 4;
         S.mbar = p;  p += kTmaChunks * 8;
@@ -646,9 +661,10 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         S.emTag = p;
     }
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    // Role of this warp: 0 = hash/extend pool, 1 = long table, 2 = short table, 3 / 4 = entries of the first /
+    // Role of this warp: 0 = hash/extend pool, 1 = bucket counters (T), 2 = spare, 3 / 4 = entries of the first /
     // second half window (P1), 5 / 6 = emit of the first / second half window (P2).
     const uint32_t role = warp < kEhWarps ? 0u : warp - kEhWarps + 1u;
+    uint32_t *sorted = P.sorted + static_cast<size_t>(blockIdx.x) * kSortedCap;
 
     if (tid == 0) {
         for (uint32_t c = 0; c < kTmaChunks; c++) mbar_init(S.mbar + c * 8u, 1);
@@ -675,8 +691,9 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         uint4 *out = P.seqs + static_cast<uint64_t>(b) * P.seqStride;
         const uint32_t bulk = n & ~15u;
         const uint32_t nChunks = (bulk + kTmaChunk - 1) / kTmaChunk;
+        const uint32_t nh = n >= 8 ? n - 7 : 0;
 
-        // ---- stage the block: TMA bulk copies (one elected thread) + ragged tail + table reset
+        // ---- stage the block: TMA bulk copies (one elected thread) + ragged tail; clear histogram and bitmap
         if (tid == 0) {
             fence_proxy_async();               // earlier generic-proxy reads of the buffer are done
             for (uint32_t c = 0; c < nChunks; c++) {
@@ -685,18 +702,69 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 mbar_expect_tx(bar, bytes);
                 tma_load_1d(S.in + c * kTmaChunk, gsrc + c * kTmaChunk, bytes, bar);
             }
+            sts32(S.hits, 0u);
+            sts32(S.hits + 4u, chance_threshold(nh));
         }
         if (tid >= 32 && tid < 32 + (n - bulk))
             sts8(S.in + bulk + tid - 32, gsrc[bulk + tid - 32]);
-        for (uint32_t i = tid; i < (kSmemTabL + kSmemTabS) / 16; i += kThreads)    // tabL and tabS are contiguous
-            sts128(S.tabL + i * 16u, 0xFFFFFFFFu);
+        for (uint32_t i = tid; i < (kSmemTabL + kBitmapBits / 8) / 16; i += kThreads)    // the table and the bitmap are contiguous
+            sts128(S.tab + i * 16u, 0u);
         if (tid < 2) sts32(S.task + tid * 4u, kEhWarps);
         if (tid == 2) { sts32(S.curTag, 0u); sts32(S.ecTag, 0u); sts32(S.emTag, 0u); }
+        for (uint32_t c = 0; c < nChunks; c++) mbar_wait(S.mbar + c * 8u, (tmaParity >> c) & 1u);
+        tmaParity ^= (1u << nChunks) - 1u;     // only the barriers armed for this block changed phase
         __syncthreads();
 
-        const uint32_t nh = n >= 8 ? n - 7 : 0;
+        // ---- phase A: histogram of the key buckets + repeated-key bitmap, all warps, any order
+        {
+            const uint32_t ltMask = (1u << lane) - 1u;
+            uint32_t hits = 0;
+            for (uint32_t g = warp; g * 32u < nh; g += kNumWarps) {
+                const uint32_t p = g * 32u + lane;
+                const bool valid = p < nh;
+                const uint32_t a = S.in + (p & ~3u), sh = (p & 3u) * 8u;
+                const uint32_t w0 = lds32(a), w1 = lds32(a + 4u), w2 = lds32(a + 8u);
+                const uint32_t v = key_hash(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), P.keyMask);
+                const uint32_t bkt = v >> (32 - kBucketBits);
+                const uint32_t m = __match_any_sync(0xFFFFFFFFu, valid ? bkt : (0x10000u | lane));
+                if (valid && (m & ltMask) == 0u)
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(S.tab + bkt * 4u), "r"(__popc(m)) : "memory");
+                const uint32_t bi = __umulhi(v, kBitmapBits);
+                uint32_t old = 0;
+                if (valid) asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(S.bitmap + (bi >> 5) * 4u), "r"(1u << (bi & 31u)) : "memory");
+                hits += __popc(__ballot_sync(0xFFFFFFFFu, valid && ((old >> (bi & 31u)) & 1u)));
+            }
+            if (lane == 0 && hits) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(S.hits), "r"(hits) : "memory");
+        }
+        __syncthreads();
+        if (lds32(S.hits) < lds32(S.hits + 4u)) {
+            // no more repeated keys than chance: one literal run (/root/reference/src/qatseqprod.c:1308-1313)
+            if (tid == 0) { out[0] = make_uint4(0u, n, 0u, 0u); P.counts[b] = 1u; }
+            continue;
+        }
+        // ---- bucket segment starts: exclusive scan of the histogram, in units of kSegAlign entries
+        {
+            uint32_t seg[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { seg[i] = sum; sum += (lds32(S.tab + (tid * 8u + i) * 4u) + kSegAlign - 1u) / kSegAlign; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= static_cast<uint32_t>(d)) incl += o;
+            }
+            if (lane == 31) sts32(S.scan + warp * 4u, incl);
+            __syncthreads();
+            uint32_t base = lane < warp ? lds32(S.scan + lane * 4u) : 0u;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) base += __shfl_xor_sync(0xFFFFFFFFu, base, d);
+            base += incl - sum;
+#pragma unroll
+            for (int i = 0; i < 8; i++) sts32(S.tab + (tid * 8u + i) * 4u, (base + seg[i]) << 17);
+        }
+        __syncthreads();
+
         const uint32_t nW = (n + kWindow - 1) / kWindow;
-        uint32_t chunksSeen = 0;
         EmitCarry ec = {0, 0, 0};              // P2 (loaded from / published to shared memory every half window)
 
 #ifdef B200SP_ROLE_PROFILE
@@ -707,13 +775,8 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
             const unsigned long long c0 = clock64();
 #endif
             if (role == 0u) {
-                // bytes this stage may touch: hashing window t reads < (t+1)*1024 + 11, extending
-                // window t-2 reads < (t-1)*1024 + extCap + 36 + 3
-                const uint32_t need = min(bulk, (t + 1) * kWindow + 16u);
-                const uint32_t wantChunks = (need + kTmaChunk - 1) / kTmaChunk;
-                while (chunksSeen < wantChunks) { mbar_wait(S.mbar + chunksSeen * 8u, (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
-                // One task queue per stage.  Task g extends group g of window t-2 and, inside its probe block,
-                // hashes group g of window t (the MATCH.ANY latency hides behind the candidate loads).
+                // One task queue per stage.  Task g scans and extends group g of window t-2 and, behind its first
+                // loads, hashes group g of window t.
                 const uint32_t nE = (t >= 2 && t - 2 < nW) ? kGroups : 0u;
                 // hash-only tasks exist only while there is no extension work yet (the first two stages)
                 const uint32_t nAll = nE ? nE : (t < nW ? kGroups / kHashGroups : 0u);
@@ -725,18 +788,18 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                         const uint32_t wdx = t - 2;
                         // past the last window the fused hash runs with no valid position (harmless ring writes)
                         stage_extend<true>(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap,
-                                           t, t < nW ? nh : 0u, P.shortMask);
+                                           P.scan, P.keyMask, sorted, t, t < nW ? nh : 0u);
                     } else {
                         uint32_t gs[kHashGroups];
 #pragma unroll
                         for (uint32_t i = 0; i < kHashGroups; i++) gs[i] = id - nE + i * (kGroups / kHashGroups);
-                        stage_hash<kHashGroups>(S, t, gs, lane, nh, P.shortMask);
+                        stage_hash<kHashGroups>(S, t, gs, lane, nh, P.keyMask);
                     }
                 }
             } else if (role == 1u) {
-                if (t >= 1 && t - 1 < nW) stage_table(S, S.tabL, 0u, t - 1, lane);
+                if (t >= 1 && t - 1 < nW) stage_table(S, t - 1, lane, sorted);
             } else if (role == 2u) {
-                if (t >= 1 && t - 1 < nW) stage_table(S, S.tabS, 1u, t - 1, lane);
+                // spare warp
             } else if (role <= 4u) {
                 if (role == 3u && lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, kEhWarps);   // next stage's queue (nobody touches it now)
                 if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, role - 3u, lane, P.minMatch, P.lazyDepth);
@@ -759,9 +822,6 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
             out[ec.nOut] = make_uint4(0u, n - ec.anchor, 0u, 0u);   // trailing literals / block delimiter
             P.counts[b] = ec.nOut + 1u;
         }
-        // every issued chunk must have landed before its mbarrier is re-armed for the next block
-        if (warp == 0) while (chunksSeen < nChunks) { mbar_wait(S.mbar + chunksSeen * 8u, (tmaParity >> chunksSeen) & 1u); chunksSeen++; }
-        tmaParity ^= (1u << nChunks) - 1u;   // only the barriers armed for this block changed phase
     }
 }
 
@@ -770,12 +830,16 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
 // ------------------------------------------------------------------------------------------
 bool params_for_level(int level, ParseParams &p)
 {
+    // One parameter class per zstd strategy class; the scan width is the level-scaled search
+    // depth (the reference hands the level to its engine, /root/reference/src/qatseqprod.c:1154, and rebuilds the
+    // session when it changes, :1193-1201).  Must equal oracle/seqmodel.c:seqmodel_params_for_level.
+    static const uint32_t scanOf[13] = { 0, 4, 4, 4, 8, 32, 64, 96, 96, 128, 128, 256, 256 };
     if (level < 1 || level > 12) return false;
+    p.keyMask = level <= 4 ? 0xFFu : 0u;         // 5-byte keys for the fast/dfast classes, 4-byte keys from greedy up
+    p.scan = scanOf[level];
     p.minMatch = 4;
     p.extCap = kMaxExtCap;
-    if (level <= 2)      { p.shortMask = 0xFFFFu; p.lazyDepth = 0; }   // fast class
-    else if (level <= 4) { p.shortMask = 0xFFu;   p.lazyDepth = 1; }   // dfast class
-    else                 { p.shortMask = 0u;      p.lazyDepth = 2; }   // greedy/lazy/btlazy2 classes
+    p.lazyDepth = level <= 4 ? 1 : 2;
     return true;
 }
 

@@ -174,6 +174,9 @@ struct b200sp_engine {
     cudaEvent_t evIn[kMaxChunks], evParsed[kMaxChunks], evDone[kMaxChunks];
     unsigned int *d_work;        // dynamic scheduler counter (+ developer role counters)
     unsigned int *d_chunkWork;   // [kMaxChunks] scheduler counters of the pipelined host path
+    // the parser's sorted-table scratch (b200sp::kSortedCap entries per CTA), one area per stream that can hold a
+    // launch in flight: [0] the engine's / the caller's stream, [1], [2] the two parser streams of the host path
+    uint32_t *d_sorted[3]; size_t d_sortedCap[3];
     // host-path scratch (grown on demand)
     uint8_t *d_src;      size_t d_srcCap;
     uint4 *d_seqs;       size_t d_seqsCap;      // entries
@@ -278,6 +281,7 @@ void b200sp_engine_destroy(b200sp_engine *e)
         if (e->evDone[k]) cudaEventDestroy(e->evDone[k]);
     }
     cudaFree(e->d_chunkWork);
+    for (int i = 0; i < 3; i++) cudaFree(e->d_sorted[i]);
     free(e->h_goffsets);
     cudaFree(e->d_work); cudaFree(e->d_src); cudaFree(e->d_seqs); cudaFree(e->d_counts);
     cudaFree(e->d_offsets); cudaFree(e->d_packed);
@@ -305,7 +309,7 @@ static int check_batch(const void *d_src, uint32_t blockSize, uint64_t stride, c
 static int launch_batch(b200sp_engine *e, const void *d_src, uint64_t totalSize, uint32_t blockSize,
                         uint64_t stride, const uint32_t *d_sizes, uint32_t nBlocks, int level,
                         b200sp_sequence *d_seqs, uint64_t seqStride, uint32_t *d_counts, cudaStream_t st,
-                        unsigned int *workCounter)
+                        unsigned int *workCounter, int scratch)
 {
     if (!e) return fail(B200SP_EINVAL, "null engine");
     b200sp::ParseParams p;
@@ -316,6 +320,17 @@ static int launch_batch(b200sp_engine *e, const void *d_src, uint64_t totalSize,
     if (nBlocks == 0) return B200SP_OK;
     if (!d_seqs || !d_counts) return fail(B200SP_EINVAL, "null output");
     CU_TRY(cudaSetDevice(e->device), "cudaSetDevice");
+    {
+        const uint32_t grid = nBlocks < static_cast<uint32_t>(e->numSMs) ? nBlocks : static_cast<uint32_t>(e->numSMs);
+        const size_t want = static_cast<size_t>(grid) * b200sp::kSortedCap;
+        if (want > e->d_sortedCap[scratch]) {       // cudaFree waits for launches still using the old area
+            cudaFree(e->d_sorted[scratch]);
+            e->d_sorted[scratch] = nullptr; e->d_sortedCap[scratch] = 0;
+            CU_TRY(cudaMalloc(&e->d_sorted[scratch], want * sizeof(uint32_t)), "cudaMalloc(sorted-table scratch)");
+            e->d_sortedCap[scratch] = want;
+        }
+        p.sorted = e->d_sorted[scratch];
+    }
     p.src = static_cast<const uint8_t *>(d_src);
     p.stride = stride;
     p.totalSize = totalSize;
@@ -341,7 +356,7 @@ int b200sp_parse_device(b200sp_engine *e, const void *d_src, uint64_t totalSize,
     if (!e) return fail(B200SP_EINVAL, "null engine");
     cudaStream_t st = cudaStream ? static_cast<cudaStream_t>(cudaStream) : e->stream;
     return launch_batch(e, d_src, totalSize, blockSize, stride, d_sizes, nBlocks, level, d_seqs, seqStride, d_counts, st,
-                        e->d_work);
+                        e->d_work, 0);
 }
 
 int b200sp_verify_device(b200sp_engine *e, const void *d_src, uint64_t totalSize, uint32_t blockSize,
@@ -472,7 +487,7 @@ int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint3
         uint32_t *dcounts = e->d_counts + b0;
         unsigned long long *doffs = e->d_offsets + b0 + k;
         int rc = launch_batch(e, dsrc, totalStrided, blockSize, stride, nullptr, static_cast<uint32_t>(nb), level,
-                              reinterpret_cast<b200sp_sequence *>(dseqs), seqStride, dcounts, sp, e->d_chunkWork + k);
+                              reinterpret_cast<b200sp_sequence *>(dseqs), seqStride, dcounts, sp, e->d_chunkWork + k, 1 + (k & 1));
         if (rc) return rc;
         CU_TRY(cudaEventRecord(e->evParsed[k], sp), "event record");
         CU_TRY(cudaStreamWaitEvent(e->sPost, e->evParsed[k], 0), "stream wait");
@@ -586,7 +601,7 @@ int b200sp_parse_staged(b200sp_engine *e, const uint32_t *sizes, uint32_t nBlock
     }
     int rc = launch_batch(e, dBlocks, static_cast<uint64_t>(nBlocks) * stride, B200SP_BLOCK_MAX, stride,
                           reinterpret_cast<const uint32_t *>(dSizes), nBlocks, level,
-                          reinterpret_cast<b200sp_sequence *>(e->d_seqs), seqStride, e->d_counts, st, e->d_work);
+                          reinterpret_cast<b200sp_sequence *>(e->d_seqs), seqStride, e->d_counts, st, e->d_work, 0);
     if (rc) return rc;
     scan_counts_kernel<<<1, 32, 0, st>>>(e->d_counts, nBlocks, e->d_offsets);
     CU_TRY(cudaGetLastError(), "launch scan_counts_kernel");
