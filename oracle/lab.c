@@ -356,7 +356,7 @@ int main(int argc, char **argv)
     L.gainMode = env_int("LAB_GAINMODE", 0); L.backExt = env_int("LAB_BACKEXT", 0); L.skipBonus = env_int("LAB_SKIPBONUS", 0); L.repTie = env_int("LAB_REPTIE", 0); L.repLong = env_int("LAB_REPLONG", 1); L.seqRep = env_int("LAB_SEQREP", 0); L.follow = env_int("LAB_FOLLOW", 0); g_hbytes = env_int("LAB_HBYTES", 4); L.harm = env_int("LAB_HARM", 0); L.repK0 = env_int("LAB_REPK0", 1); L.followMin = env_int("LAB_FOLLOWMIN", 8);
     g_useModel = env_int("LAB_MODEL", 0);
     seqmodel_params_for_level(level, &g_prm);
-    g_prm.keyBytes = env_int("MODEL_KEYBYTES", g_prm.keyBytes); g_prm.scan = env_int("MODEL_SCAN", g_prm.scan);
+    g_prm.keyBytes = env_int("MODEL_KEYBYTES", g_prm.keyBytes); g_prm.rank16 = env_int("MODEL_RANK16", g_prm.rank16); g_prm.scan = env_int("MODEL_SCAN", g_prm.scan);
     g_prm.lazyDepth = env_int("MODEL_LAZY", g_prm.lazyDepth); g_prm.backExt = env_int("MODEL_BACKEXT", g_prm.backExt);
     g_prm.minMatch = env_int("MODEL_MINMATCH", g_prm.minMatch); g_prm.extCap = env_int("MODEL_EXTCAP", g_prm.extCap);
     size_t calls, errs; int ok;

@@ -12,7 +12,8 @@
  *                  that hash, most recent last).  The candidates of p are the `scan` entries before it in
  *                  its bucket whose tag equals its own, most recent first: the level-scaled search depth.
  *   2. extension   every candidate is measured in full (common prefix of src[p..] and src[cand..], up to
- *                  extCap and never past n); the longest wins, the nearer one on ties.  Then a position
+ *                  extCap and never past n); the longest wins, the nearer one on ties.  The fast classes
+ *                  (levels 1-4) rank candidates on their first 16 bytes and extend the winner only.  Then a position
  *                  adopts its right neighbour's match when that match also holds one byte earlier
  *                  (zstd's "catch up" by one; never across a 32-position group).
  *   3. propagation B(p) = the match, among all starting at q <= p, that reaches farthest right.
@@ -26,6 +27,7 @@
 #include <string.h>
 
 #define MODEL_MAX_BLOCK (1u << 17)
+#define MODEL_PROBE     16u          /* bytes a fast-class candidate is ranked on */
 
 static inline uint32_t rd32(const uint8_t *p)
 {
@@ -46,7 +48,8 @@ void seqmodel_params_for_level(int level, SeqModelParams *prm)
     static const int scanOf[13] = { 0, 4, 4, 4, 8, 32, 64, 96, 96, 128, 128, 256, 256 };
     if (level < 1) level = 1;
     if (level > 12) level = 12;
-    prm->keyBytes = level <= 4 ? 5 : 4;
+    prm->keyBytes = level == 1 ? 6 : level <= 4 ? 5 : 4;
+    prm->rank16 = level <= 4 ? 1 : 0;
     prm->scan = scanOf[level];
     prm->minMatch = 4;
     prm->extCap = 256;
@@ -105,9 +108,15 @@ int seqmodel_own_matches(const uint8_t *src, size_t n, const SeqModelParams *prm
                 if ((e >> 17) != tag) continue;
                 const uint32_t q = e & 0x1FFFFu;
                 const uint8_t *a = src + p, *c = src + q;
+                const uint32_t stop = prm->rank16 && lim > MODEL_PROBE ? MODEL_PROBE : lim;   /* fast classes rank on 16 bytes */
                 uint32_t ml = 0;
-                while (ml < lim && a[ml] == c[ml]) ml++;
+                while (ml < stop && a[ml] == c[ml]) ml++;
+                if (prm->rank16 && ml < 4) ml = 0;
                 if (ml > bestLen) { bestLen = ml; bestOff = p - q; }      /* ties keep the nearer candidate */
+            }
+            if (prm->rank16 && bestLen == MODEL_PROBE) {                  /* ... and extend only the winner */
+                const uint8_t *a = src + p, *c = src + p - bestOff;
+                while (bestLen < lim && a[bestLen] == c[bestLen]) bestLen++;
             }
             if (bestLen < (uint32_t)prm->minMatch) bestLen = 0;
         }

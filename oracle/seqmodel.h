@@ -34,6 +34,7 @@ extern "C" {
 typedef struct {
     int keyBytes;     /* bytes hashed into the bucket key: 4, 5 or 6                                       */
     int scan;         /* bucket entries examined per position, most recent first (the level-scaled depth)  */
+    int rank16;       /* 1: candidates are ranked on their first 16 bytes, only the winner is extended      */
     int minMatch;     /* shortest match the parser may emit (>= 3)                                         */
     int extCap;       /* per-position match length cap in bytes (<= 256)                                   */
     int lazyDepth;    /* 0 greedy, 1 lazy, 2 lazy2                                                         */

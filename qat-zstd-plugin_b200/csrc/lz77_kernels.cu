@@ -38,6 +38,7 @@
 #define B200SP_SPIN_NS 100
 #endif
 
+
 namespace b200sp {
 
 // ------------------------------------------------------------------------------------------
@@ -154,7 +155,8 @@ struct Shared {         // 32-bit shared-window addresses
     uint32_t in;        // the staged block (+ pad)
     uint32_t tab;       // u32[kBuckets]        phase A: histogram; then {segment start / 8 : 15 | entries so far : 17}
     uint32_t bitmap;    // kBitmapBits bits     phase A only: overlays the spare table and the rings
-    uint32_t ringH;     // u32[2][kWindow]      H -> T: {valid:1 | bucket:13 | tag:15}
+    uint32_t ringH;     // u32[2][kWindow]      H -> T: {valid:1 | lanes in the bucket - 1:5 | first such lane:5 | earlier such lanes:5 | bucket:13}
+    uint32_t ringT;     // u16[2][kWindow]      H -> T: tag (in the spare table)
     uint32_t ringC;     // u32[kRingC][kWindow] {slot in the sorted table:18 | insertion index (capped):14} (T) -> packed prefix maxima (E)
     uint32_t ringL;     // u32[2][kWindow]      P1 -> P2: memoised decisions {end:9 | take lane:5 | offset:17}
     uint32_t gmax;      // u32[kRingC][kGroups] packed farthest-reaching match of each group
@@ -181,61 +183,90 @@ __device__ __forceinline__ uint32_t key_hash(uint32_t lo, uint32_t hi, uint32_t 
     return lo * 0x9E3779B1u + (hi & keyMask) * 0xC2B2AE3Du;
 }
 
-template <int N>      // N groups per task, interleaved by hand
-__device__ __forceinline__ void stage_hash(const Shared &S, uint32_t w, const uint32_t (&group)[N], uint32_t lane,
-                                           uint32_t nh, uint32_t keyMask)
+// In two halves: MATCH.ANY takes a long time to come back, so a task starts the hash of its group early
+// (hash_begin) and writes the ring words when its own work is done (hash_finish).
+struct HashState { uint32_t v, m; };
+
+__device__ __forceinline__ HashState hash_begin(const Shared &S, uint32_t w, uint32_t group, uint32_t lane, uint32_t nh, uint32_t keyMask)
 {
-    uint32_t p[N], w0[N], w1[N], w2[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        p[i] = w * kWindow + group[i] * 32u + lane;
-        const uint32_t a = S.in + (min(p[i], kBlockMax) & ~3u);       // reads stay inside the padded buffer
-        w0[i] = ldsc32(a); w1[i] = ldsc32(a + 4u); w2[i] = ldsc32(a + 8u);
-    }
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        const uint32_t sh = (p[i] & 3u) * 8u;
-        const uint32_t lo = __funnelshift_r(w0[i], w1[i], sh);
-        const uint32_t hi = __funnelshift_r(w1[i], w2[i], sh);
-        const uint32_t v = key_hash(lo, hi, keyMask);
-        sts32(S.ringH + (w & 1u) * (kWindow * 4u) + ring_byte(group[i], lane), p[i] < nh ? (v >> 4) | (1u << 28) : 0u);
-    }
+    const uint32_t p = w * kWindow + group * 32u + lane;
+    const uint32_t a = S.in + (min(p, kBlockMax) & ~3u), sh = (p & 3u) * 8u;       // reads stay inside the padded buffer
+    const uint32_t w0 = ldsc32(a), w1 = ldsc32(a + 4u), w2 = ldsc32(a + 8u);
+    HashState h;
+    h.v = key_hash(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), keyMask);
+    // lanes of the group in the same bucket (invalid lanes get unique keys so they never pair up)
+    h.m = __match_any_sync(0xFFFFFFFFu, p < nh ? h.v >> (32 - kBucketBits) : (0x10000u | lane));
+    return h;
+}
+
+__device__ __forceinline__ void hash_finish(const Shared &S, uint32_t w, uint32_t group, uint32_t lane, uint32_t nh, const HashState &h)
+{
+    // everything the table warp needs, so that it has as few instructions of its own as possible:
+    // {valid:1 | lanes in the bucket - 1 : 5 | their first lane : 5 | earlier lanes in the bucket : 5 | bucket : 13}
+    const uint32_t p = w * kWindow + group * 32u + lane;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const uint32_t word = (h.v >> (32 - kBucketBits)) | (__popc(h.m & ltMask) << 13) | ((__ffs(h.m) - 1) << 18) |
+                          ((__popc(h.m) - 1) << 23) | (1u << 28);
+    const uint32_t rb = ring_byte(group, lane);
+    sts32(S.ringH + (w & 1u) * (kWindow * 4u) + rb, p < nh ? word : 0u);
+    sts16(S.ringT + (w & 1u) * (kWindow * 2u) + (rb >> 1), (h.v >> 4) & 0x7FFFu);
 }
 
 // ------------------------------------------------------------------------------------------
 // T: one warp walks the window group by group, in position order.  A position's insertion index in its bucket is
-// the bucket's counter plus the number of earlier lanes of the group with the same bucket (MATCH.ANY); the last
-// such lane adds the multiplicity to the counter: exact serial semantics.  The position goes into its slot of the
-// sorted table (global scratch; read by the pool one stage later), slot and index go to the pool through ringC.
+// the bucket's counter plus the number of earlier lanes of the group with the same bucket (MATCH.ANY); the first
+// such lane adds the multiplicity to the counter with one shared-memory atomic and hands the old value to the
+// others.  The atomics of consecutive groups are issued back to back (the unit applies them in order; nothing
+// waits for a value before the next one is issued), so the walk is a stream, not a chain of round trips.
+// The position goes into its slot of the sorted table (global scratch; read by the pool one stage later); slot
+// and index go to the pool through ringC.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void stage_table(const Shared &S, uint32_t w, uint32_t lane, uint32_t *sorted)
 {
+    // kTUnroll groups per iteration: all their ring words are loaded, then all their atomics issued, before the
+    // first result is needed - the walk pays the shared-memory latency once per iteration, not per group.  A lone
+    // warp issues an instruction every several cycles: the hash tasks have prepared everything they could.
+#ifdef B200SP_T_UNROLL
+    constexpr uint32_t kTUnroll = B200SP_T_UNROLL;
+#else
+    constexpr uint32_t kTUnroll = 4;
+#endif
+    static_assert(kGroups % kTUnroll == 0, "the table warp walks whole iterations");
     const uint32_t rh = S.ringH + (w & 1u) * (kWindow * 4u);
+    const uint32_t rt = S.ringT + (w & 1u) * (kWindow * 2u);
     const uint32_t rc = S.ringC + (w & (kRingC - 1)) * (kWindow * 4u);
     const uint32_t windowBase = w * kWindow;
-    const uint32_t ltMask = (1u << lane) - 1u;
-    const uint32_t geMask = ~((2u << lane) - 1u);      // lanes strictly above
 #pragma unroll 1
-    for (uint32_t g0 = 0; g0 < kGroups; g0 += 4) {
-        uint32_t hw[4], m[4];
+    for (uint32_t g0 = 0; g0 < kGroups; g0 += kTUnroll) {
+        uint32_t hw[kTUnroll], tg[kTUnroll], old[kTUnroll];
 #pragma unroll
-        for (int k = 0; k < 4; k++)      // groups past the window's end: invalid
-            hw[k] = g0 + k < kGroups ? lds32(rh + ring_byte(g0 + k, lane)) : 0u;
+        for (uint32_t k = 0; k < kTUnroll; k++) {
+            const uint32_t rb = ring_byte(g0 + k, lane);
+            hw[k] = lds32(rh + rb);
+            tg[k] = lds16(rt + (rb >> 1));
+        }
 #pragma unroll
-        for (int k = 0; k < 4; k++)      // invalid lanes get unique keys so they never pair up
-            m[k] = __match_any_sync(0xFFFFFFFFu, (hw[k] >> 28) ? (hw[k] >> 15) & (kBuckets - 1u) : (0x10000u | lane));
+        for (uint32_t k = 0; k < kTUnroll; k++) {
+            // the first lane of each bucket adds the bucket's multiplicity to its counter (the 17-bit counter never
+            // carries into the start); predicated, not branched: the atomics of the iteration stream back to back
+            asm volatile(
+                "{\n\t.reg .pred q;\n\t"
+                "setp.ne.u32 q, %3, 0;\n\t"
+                "mov.u32 %0, 0;\n\t"
+                "@q atom.shared.add.u32 %0, [%1], %2;\n\t}"
+                : "=r"(old[k])
+                : "r"(S.tab + (hw[k] & (kBuckets - 1u)) * 4u), "r"(((hw[k] >> 23) & 31u) + 1u),
+                  "r"(static_cast<uint32_t>((hw[k] >> 28) != 0u && ((hw[k] >> 18) & 31u) == lane))
+                : "memory");
+        }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (uint32_t k = 0; k < kTUnroll; k++) {
             const bool valid = (hw[k] >> 28) != 0u;
-            const uint32_t ta = S.tab + ((hw[k] >> 15) & (kBuckets - 1u)) * 4u;
-            const uint32_t rank = __popc(m[k] & ltMask);
-            const uint32_t e = lds32(ta);
-            if (valid && (m[k] & geMask) == 0u) sts32(ta, e + rank + 1u);   // the 17-bit counter never carries into the start
-            __syncwarp();       // orders this group's stores before the next group's loads
-            const uint32_t idx = (e & 0x1FFFFu) + rank;
+            const uint32_t e = __shfl_sync(0xFFFFFFFFu, old[k], (hw[k] >> 18) & 31u);
+            const uint32_t idx = (e & 0x1FFFFu) + ((hw[k] >> 13) & 31u);
             const uint32_t slot = (e >> 17) * kSegAlign + idx;
-            if (valid) sorted[slot] = (windowBase + (g0 + k) * 32u + lane) | ((hw[k] & 0x7FFFu) << 17);
-            if (g0 + k < kGroups) sts32(rc + ring_byte(g0 + k, lane), valid ? (slot << 14) | min(idx, kIdxCap) : 0u);
+            if (valid) sorted[slot] = (windowBase + (g0 + k) * 32u + lane) | (tg[k] << 17);
+            sts32(rc + ring_byte(g0 + k, lane), valid ? (slot << 14) | min(idx, kIdxCap) : 0u);
         }
     }
 }
@@ -244,14 +275,29 @@ __device__ __forceinline__ void stage_table(const Shared &S, uint32_t w, uint32_
 // E: bucket scan of one group -> best match per position -> prefix-max of match ends
 // ringC out: packed prefix maximum {end - groupStart:9 | 31 - lane:6 | offset:17} (0 = none so far)
 // ------------------------------------------------------------------------------------------
+#ifndef B200SP_ALU_DIFF
+#define B200SP_ALU_DIFF 0
+#endif
+// index (0..3) of the lowest non-zero byte of x != 0.  FLO/BREV share the memory-instruction queue with the
+// shared-memory loads this stage is made of; three compares on the isolated lowest bit stay in the ALU.
+__device__ __forceinline__ uint32_t low_byte_index(uint32_t x)
+{
+#if B200SP_ALU_DIFF
+    const uint32_t low = x & (0u - x);
+    return (low > 0xFFu ? 1u : 0u) + (low > 0xFFFFu ? 1u : 0u) + (low > 0xFFFFFFu ? 1u : 0u);
+#else
+    return (__ffs(x) - 1) >> 3;
+#endif
+}
+
 __device__ __forceinline__ uint32_t first_diff_16(uint32_t x1, uint32_t x2, uint32_t x3)
 {
     // length of the common prefix of two 16-byte strings whose first 4 bytes are equal,
     // given the XOR of words 1..3 (branch-free)
     uint32_t len = 16u;
-    if (x3) len = 12u + ((__ffs(x3) - 1) >> 3);
-    if (x2) len = 8u + ((__ffs(x2) - 1) >> 3);
-    if (x1) len = 4u + ((__ffs(x1) - 1) >> 3);
+    if (x3) len = 12u + low_byte_index(x3);
+    if (x2) len = 8u + low_byte_index(x2);
+    if (x1) len = 4u + low_byte_index(x1);
     return len;
 }
 
@@ -262,15 +308,170 @@ __device__ __forceinline__ uint4 ldg128_cg(const uint32_t *p)      // L2 only: t
     return v;
 }
 
+// Tail shared by both extension variants: "catch up" by one byte, packed prefix maximum, group words.
+__device__ __forceinline__ void finish_group(const Shared &S, uint32_t idx, uint32_t slotC, uint32_t group, uint32_t lane,
+                                             uint32_t p, uint32_t a0, uint32_t bestLen, uint32_t bestOff,
+                                             uint32_t minMatch, uint32_t extCap)
+{
+    const uint32_t in = S.in;
+    // zstd's "catch up" by one byte: adopt the right neighbour's match if it also holds one byte earlier
+    {
+        const uint32_t l1 = __shfl_down_sync(0xFFFFFFFFu, bestLen, 1), o1 = __shfl_down_sync(0xFFFFFFFFu, bestOff, 1);
+        const bool cand = lane < 31u && l1 != 0u && p >= o1 && l1 + 1u > bestLen && l1 + 1u <= extCap;
+        const uint32_t back = cand ? lds32(in + ((p - o1) & ~3u)) >> (((p - o1) & 3u) * 8u) : ~a0;
+        if (cand && ((back ^ a0) & 0xFFu) == 0u) { bestLen = l1 + 1u; bestOff = o1; }
+    }
+    // Pack {end relative to the group start (9 bits), 31 - lane (6 bits), offset (17 bits)}: an unsigned
+    // max over packed words picks the farthest-reaching match and, on ties, the older one.
+    uint32_t pk = 0;
+    if (bestLen) pk = ((lane + bestLen) << 23) | ((31u - lane) << 17) | bestOff;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pk, d);
+        if (lane >= static_cast<uint32_t>(d)) pk = max(pk, o);
+    }
+    sts32(idx, pk);                                      // prefix-max within the group
+    const uint32_t own = __ballot_sync(0xFFFFFFFFu, (pk >> 23) >= lane + minMatch);
+    if (lane == 31) { sts32(S.gmax + (slotC * 64u + group) * 4u, pk); sts32(S.gown + (slotC * 64u + group) * 4u, own); }
+}
+
+__device__ __forceinline__ uint32_t ldg32_cg(const uint32_t *p)       // L2 only: the entries were stored by the table warp a stage ago
+{
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// e[j] = entry (s - 1 - j) out of the two aligned chunks around it; t = (s - 1) & 3 is the place of s-1 in `hi`.
+// As one array r = {lo.x .. lo.w, hi.x .. hi.w}: e[j] = r[t + 4 - j], a window of four moved by t: two levels of selects.
+__device__ __forceinline__ void pick4(const uint4 &hi, const uint4 &lo, uint32_t t, uint32_t (&e)[4])
+{
+    const bool b0 = (t & 1u) != 0u, b1 = (t & 2u) != 0u;
+    const uint32_t a0 = b0 ? lo.z : lo.y, a1 = b0 ? lo.w : lo.z, a2 = b0 ? hi.x : lo.w;
+    const uint32_t a3 = b0 ? hi.y : hi.x, a4 = b0 ? hi.z : hi.y, a5 = b0 ? hi.w : hi.z;
+    e[3] = b1 ? a2 : a0;
+    e[2] = b1 ? a3 : a1;
+    e[1] = b1 ? a4 : a2;
+    e[0] = b1 ? a5 : a3;
+}
+
+// Fast classes (levels 1-4): the `scan` (4 or 8) entries before the position are probed branch-free on their first
+// 16 bytes, four at a time; the longest probe wins (the nearer one on ties) and only the winner is extended: lanes
+// continuing their predecessor's match derive their length from the run head, heads are extended by the whole warp.
 template <bool kFuseHash>
-__device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32_t group, uint32_t lane,
+__device__ __forceinline__ void stage_extend_fast(const Shared &S, uint32_t w, uint32_t group, uint32_t lane,
+                                                  uint32_t p, uint32_t n, uint32_t nh, uint32_t minMatch,
+                                                  uint32_t extCap, uint32_t scan, uint32_t keyMask, const uint32_t *sorted,
+                                                  uint32_t hashWindow = 0, uint32_t hashNh = 0)
+{
+    const uint32_t slotC = w & (kRingC - 1);
+    const uint32_t idx = S.ringC + slotC * (kWindow * 4u) + ring_byte(group, lane);
+    const uint32_t cw = lds32(idx);       // ordered load: the first task's address is known before the stage barrier, and this word was written in the stage before
+    const uint32_t in = S.in;
+    const bool valid = p < nh;
+    const uint32_t lim = valid ? min(n - p, extCap) : 0u;
+    const uint32_t probe = min(lim, kProbe);
+    const uint32_t s = cw >> 14;
+    const uint32_t avail = valid ? min(scan, cw & 0x3FFFu) : 0u;
+    // the four entries before us, s-1 .. s-4, lie in the aligned 16-byte chunk holding s-1 and in the one before it
+    // (two loads of one sector per lane instead of four)
+    const uint32_t cHi = avail ? (s - 1u) >> 2 : 0u;
+    uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = make_uint4(0u, 0u, 0u, 0u);
+    if (avail) hi = ldg128_cg(sorted + 4u * cHi);
+    if (avail > ((s - 1u) & 3u) + 1u) lo = ldg128_cg(sorted + 4u * (cHi - 1u));      // only when `hi` does not hold all of them
+    // our own first 16 bytes, as four unaligned words (reads stay inside the padded buffer)
+    uint32_t a0, a1, a2, a3;
+    {
+        const uint32_t a = in + (min(p, kBlockMax) & ~3u), sh = (p & 3u) * 8u;
+        const uint32_t x0 = ldsc32(a), x1 = ldsc32(a + 4u), x2 = ldsc32(a + 8u), x3 = ldsc32(a + 12u), x4 = ldsc32(a + 16u);
+        a0 = __funnelshift_r(x0, x1, sh); a1 = __funnelshift_r(x1, x2, sh);
+        a2 = __funnelshift_r(x2, x3, sh); a3 = __funnelshift_r(x3, x4, sh);
+    }
+    HashState hs = {0u, 0u};
+    if (kFuseHash) hs = hash_begin(S, hashWindow, group, lane, hashNh, keyMask);    // finished at the end of the task
+    const uint32_t tag = (key_hash(a0, a1, keyMask) >> 4) & 0x7FFFu;
+    uint32_t bestLen = 0, bestOff = 0;
+    uint32_t e[4];
+    pick4(hi, lo, (s - 1u) & 3u, e);
+#pragma unroll 1
+    for (uint32_t base = 0; base < scan; base += 4u) {
+        uint32_t q[4];
+        bool ok[4];
+        uint32_t yy[4][5];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            ok[j] = base + j < avail && (e[j] >> 17) == tag;
+            q[j] = ok[j] ? e[j] & 0x1FFFFu : 0u;
+            const uint32_t qa = in + (q[j] & ~3u);
+#pragma unroll
+            for (int k = 0; k < 5; k++) yy[j][k] = ldsc32(qa + 4u * k);
+        }
+        uint4 hi2 = make_uint4(0u, 0u, 0u, 0u), lo2 = hi2;
+        const uint32_t s2 = s - 4u - base;      // next round: entries s2-1 .. s2-4
+        const bool more = base + 4u < scan && base + 4u < avail;
+        if (more) {                      // in flight while we measure
+            const uint32_t c2 = (s2 - 1u) >> 2;
+            hi2 = ldg128_cg(sorted + 4u * c2);
+            if (avail - base - 4u > ((s2 - 1u) & 3u) + 1u) lo2 = ldg128_cg(sorted + 4u * (c2 - 1u));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {    // most recent first: a farther candidate must be strictly longer
+            const uint32_t sh = (q[j] & 3u) * 8u;
+            const uint32_t b0 = __funnelshift_r(yy[j][0], yy[j][1], sh), b1 = __funnelshift_r(yy[j][1], yy[j][2], sh);
+            const uint32_t b2 = __funnelshift_r(yy[j][2], yy[j][3], sh), b3 = __funnelshift_r(yy[j][3], yy[j][4], sh);
+            uint32_t ml = min(first_diff_16(a1 ^ b1, a2 ^ b2, a3 ^ b3), probe);
+            if (!ok[j] || b0 != a0) ml = 0;
+            if (ml > bestLen) { bestLen = ml; bestOff = p - q[j]; }
+        }
+        pick4(hi2, lo2, (s2 - 1u) & 3u, e);
+    }
+
+    // Long extension of winners that filled the probe.  A lane continuing its predecessor's
+    // match (same offset, both filled the probe) derives its length from the run head; heads are
+    // extended by the whole warp, 128 bytes per step, far enough to serve all their followers.
+    const bool job = (bestLen == kProbe) && (lim > kProbe);
+    const uint32_t prevOff = __shfl_up_sync(0xFFFFFFFFu, bestOff, 1);
+    const uint32_t jobs = __ballot_sync(0xFFFFFFFFu, job);
+    const bool follower = job && lane > 0 && ((jobs >> (lane - 1)) & 1u) && prevOff == bestOff;
+    uint32_t heads = jobs & ~__ballot_sync(0xFFFFFFFFu, follower);
+    const uint32_t myHead = job ? 31u - __clz(heads & ((2u << lane) - 1u)) : 32u;
+    while (heads) {
+        const uint32_t h = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const uint32_t ph = p - lane + h;                               // head position (uniform)
+        const uint32_t offh = __shfl_sync(0xFFFFFFFFu, bestOff, h);
+        const uint32_t qh = ph - offh;
+        const uint32_t reach = min(n - ph, extCap + 32u);               // how far any follower may need
+        uint32_t U = reach;
+#pragma unroll 1
+        for (uint32_t k0 = kProbe; k0 < reach; k0 += 128u) {
+            const uint32_t k = k0 + lane * 4u;
+            uint32_t x = 0;
+            if (k < reach) x = ld32u(in, ph + k) ^ ld32u(in, qh + k);
+            const uint32_t bad = __ballot_sync(0xFFFFFFFFu, x != 0u);
+            if (bad) {
+                const uint32_t l = __ffs(bad) - 1;
+                const uint32_t xl = __shfl_sync(0xFFFFFFFFu, x, l);
+                U = min(reach, k0 + l * 4u + ((__ffs(xl) - 1) >> 3));
+                break;
+            }
+        }
+        if (myHead == h) bestLen = min(lim, U - (lane - h));
+    }
+    if (bestLen < minMatch) { bestLen = 0; bestOff = 0; }
+    finish_group(S, idx, slotC, group, lane, p, a0, bestLen, bestOff, minMatch, extCap);
+    if (kFuseHash) hash_finish(S, hashWindow, group, lane, hashNh, hs);
+}
+
+template <bool kFuseHash>
+__device__ __forceinline__ void stage_extend_full(const Shared &S, uint32_t w, uint32_t group, uint32_t lane,
                                              uint32_t p, uint32_t n, uint32_t nh, uint32_t minMatch,
                                              uint32_t extCap, uint32_t scan, uint32_t keyMask, const uint32_t *sorted,
                                              uint32_t hashWindow = 0, uint32_t hashNh = 0)
 {
     const uint32_t slotC = w & (kRingC - 1);
     const uint32_t idx = S.ringC + slotC * (kWindow * 4u) + ring_byte(group, lane);
-    const uint32_t cw = ldsc32(idx);
+    const uint32_t cw = lds32(idx);       // ordered load: the first task's address is known before the stage barrier, and this word was written in the stage before
     const uint32_t in = S.in;
     const bool valid = p < nh;
     const uint32_t lim = valid ? min(n - p, extCap) : 0u;
@@ -290,10 +491,8 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32
     const int32_t Alast = avail ? static_cast<int32_t>(first >> 2) : 0;
     uint4 chunk = make_uint4(0u, 0u, 0u, 0u);
     if (A >= Alast) chunk = ldg128_cg(sorted + 4 * A);
-    if (kFuseHash) {        // same basic block as the first loads: their latency hides the hash
-        const uint32_t gs[1] = {group};
-        stage_hash<1>(S, hashWindow, gs, lane, hashNh, keyMask);
-    }
+    HashState hs = {0u, 0u};
+    if (kFuseHash) hs = hash_begin(S, hashWindow, group, lane, hashNh, keyMask);    // finished at the end of the task
     const uint32_t tag = (key_hash(a0, a1, keyMask) >> 4) & 0x7FFFu;
     uint32_t bestLen = 0, bestOff = 0;
     while (__any_sync(0xFFFFFFFFu, A >= Alast)) {
@@ -341,25 +540,8 @@ __device__ __forceinline__ void stage_extend(const Shared &S, uint32_t w, uint32
         }
     }
     if (bestLen < minMatch) { bestLen = 0; bestOff = 0; }
-    // zstd's "catch up" by one byte: adopt the right neighbour's match if it also holds one byte earlier
-    {
-        const uint32_t l1 = __shfl_down_sync(0xFFFFFFFFu, bestLen, 1), o1 = __shfl_down_sync(0xFFFFFFFFu, bestOff, 1);
-        const bool cand = lane < 31u && l1 != 0u && p >= o1 && l1 + 1u > bestLen && l1 + 1u <= extCap;
-        const uint32_t back = cand ? lds32(in + ((p - o1) & ~3u)) >> (((p - o1) & 3u) * 8u) : ~a0;
-        if (cand && ((back ^ a0) & 0xFFu) == 0u) { bestLen = l1 + 1u; bestOff = o1; }
-    }
-    // Pack {end relative to the group start (9 bits), 31 - lane (6 bits), offset (17 bits)}: an unsigned
-    // max over packed words picks the farthest-reaching match and, on ties, the older one.
-    uint32_t pk = 0;
-    if (bestLen) pk = ((lane + bestLen) << 23) | ((31u - lane) << 17) | bestOff;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, pk, d);
-        if (lane >= static_cast<uint32_t>(d)) pk = max(pk, o);
-    }
-    sts32(idx, pk);                                      // prefix-max within the group
-    const uint32_t own = __ballot_sync(0xFFFFFFFFu, (pk >> 23) >= lane + minMatch);
-    if (lane == 31) { sts32(S.gmax + (slotC * 64u + group) * 4u, pk); sts32(S.gown + (slotC * 64u + group) * 4u, own); }
+    finish_group(S, idx, slotC, group, lane, p, a0, bestLen, bestOff, minMatch, extCap);
+    if (kFuseHash) hash_finish(S, hashWindow, group, lane, hashNh, hs);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -634,6 +816,7 @@ __device__ __forceinline__ uint32_t chance_threshold(uint32_t nh)
     return e + 6u * r + 24u;
 }
 
+template <bool kFast>
 __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParseParams P)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -643,7 +826,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         asm volatile("mov.u32 %0, %1;" : "=r"(p) : "r"(smem_u32(smem)));   // opaque: one register, never re-derived
         S.in = p;    p += kSmemInput;
         S.tab = p;   p += kSmemTabL;
-        S.bitmap = p; p += kSmemTabS;          // the bitmap of phase A runs from here through the rings
+        S.bitmap = p; S.ringT = p; p += kSmemTabS;   // the bitmap of phase A runs from here through the rings; afterwards the tag ring lives here
         S.ringH = p; p += kSmemRingH;
         S.ringC = p; p += kSmemRingC;
         S.ringL = p; p += kSmemRingL;
@@ -664,6 +847,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
     // Role of this warp: 0 = hash/extend pool, 1 = bucket counters (T), 2 = spare, 3 / 4 = entries of the first /
     // second half window (P1), 5 / 6 = emit of the first / second half window (P2).
     const uint32_t role = warp < kEhWarps ? 0u : warp - kEhWarps + 1u;
+    const uint32_t poolIdx = warp;
     uint32_t *sorted = P.sorted + static_cast<size_t>(blockIdx.x) * kSortedCap;
 
     if (tid == 0) {
@@ -717,7 +901,6 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
 
         // ---- phase A: histogram of the key buckets + repeated-key bitmap, all warps, any order
         {
-            const uint32_t ltMask = (1u << lane) - 1u;
             uint32_t hits = 0;
             for (uint32_t g = warp; g * 32u < nh; g += kNumWarps) {
                 const uint32_t p = g * 32u + lane;
@@ -726,9 +909,9 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 const uint32_t w0 = lds32(a), w1 = lds32(a + 4u), w2 = lds32(a + 8u);
                 const uint32_t v = key_hash(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), P.keyMask);
                 const uint32_t bkt = v >> (32 - kBucketBits);
-                const uint32_t m = __match_any_sync(0xFFFFFFFFu, valid ? bkt : (0x10000u | lane));
-                if (valid && (m & ltMask) == 0u)
-                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(S.tab + bkt * 4u), "r"(__popc(m)) : "memory");
+                // one reduction per lane: lanes of the same bucket are serialised by the unit, which costs less than
+                // pairing them up first (MATCH.ANY)
+                if (valid) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(S.tab + bkt * 4u), "r"(1u) : "memory");
                 const uint32_t bi = __umulhi(v, kBitmapBits);
                 uint32_t old = 0;
                 if (valid) asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(S.bitmap + (bi >> 5) * 4u), "r"(1u << (bi & 31u)) : "memory");
@@ -744,9 +927,13 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
         }
         // ---- bucket segment starts: exclusive scan of the histogram, in units of kSegAlign entries
         {
-            uint32_t seg[8], sum = 0;
+            constexpr uint32_t kBins = (kBuckets + kThreads - 1) / kThreads;       // consecutive buckets per thread
+            uint32_t seg[kBins], sum = 0;
 #pragma unroll
-            for (int i = 0; i < 8; i++) { seg[i] = sum; sum += (lds32(S.tab + (tid * 8u + i) * 4u) + kSegAlign - 1u) / kSegAlign; }
+            for (uint32_t i = 0; i < kBins; i++) {
+                seg[i] = sum;
+                if (tid * kBins + i < kBuckets) sum += (lds32(S.tab + (tid * kBins + i) * 4u) + kSegAlign - 1u) / kSegAlign;
+            }
             uint32_t incl = sum;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -760,7 +947,8 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
             for (int d = 16; d; d >>= 1) base += __shfl_xor_sync(0xFFFFFFFFu, base, d);
             base += incl - sum;
 #pragma unroll
-            for (int i = 0; i < 8; i++) sts32(S.tab + (tid * 8u + i) * 4u, (base + seg[i]) << 17);
+            for (uint32_t i = 0; i < kBins; i++)
+                if (tid * kBins + i < kBuckets) sts32(S.tab + (tid * kBins + i) * 4u, (base + seg[i]) << 17);
         }
         __syncthreads();
 
@@ -783,17 +971,17 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 const uint32_t ctr = S.task + (t & 1u) * 4u;
                 // the first task of every pool warp is its own index (the counter starts at kEhWarps); only the
                 // later ones cost an atomic
-                for (uint32_t id = warp; id < nAll; id = pop_task(ctr, lane)) {
+                for (uint32_t id = poolIdx; id < nAll; id = pop_task(ctr, lane)) {
                     if (id < nE) {
                         const uint32_t wdx = t - 2;
                         // past the last window the fused hash runs with no valid position (harmless ring writes)
-                        stage_extend<true>(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap,
-                                           P.scan, P.keyMask, sorted, t, t < nW ? nh : 0u);
+                        if (kFast) stage_extend_fast<true>(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap,
+                                                           P.scan, P.keyMask, sorted, t, t < nW ? nh : 0u);
+                        else stage_extend_full<true>(S, wdx, id, lane, wdx * kWindow + id * 32u + lane, n, nh, P.minMatch, P.extCap,
+                                                     P.scan, P.keyMask, sorted, t, t < nW ? nh : 0u);
                     } else {
-                        uint32_t gs[kHashGroups];
-#pragma unroll
-                        for (uint32_t i = 0; i < kHashGroups; i++) gs[i] = id - nE + i * (kGroups / kHashGroups);
-                        stage_hash<kHashGroups>(S, t, gs, lane, nh, P.keyMask);
+                        const HashState hs = hash_begin(S, t, id, lane, nh, P.keyMask);
+                        hash_finish(S, t, id, lane, nh, hs);
                     }
                 }
             } else if (role == 1u) {
@@ -835,7 +1023,8 @@ bool params_for_level(int level, ParseParams &p)
     // session when it changes, :1193-1201).  Must equal oracle/seqmodel.c:seqmodel_params_for_level.
     static const uint32_t scanOf[13] = { 0, 4, 4, 4, 8, 32, 64, 96, 96, 128, 128, 256, 256 };
     if (level < 1 || level > 12) return false;
-    p.keyMask = level <= 4 ? 0xFFu : 0u;         // 5-byte keys for the fast/dfast classes, 4-byte keys from greedy up
+    p.keyMask = level == 1 ? 0xFFFFu : level <= 4 ? 0xFFu : 0u;   // 6-byte keys at level 1, 5-byte keys for the other fast/dfast levels, 4-byte keys from greedy up
+    p.rank16 = level <= 4 ? 1u : 0u;             // fast classes rank candidates on 16 bytes and extend the winner; the others measure every candidate in full
     p.scan = scanOf[level];
     p.minMatch = 4;
     p.extCap = kMaxExtCap;
@@ -845,15 +1034,17 @@ bool params_for_level(int level, ParseParams &p)
 
 cudaError_t configure_kernels()
 {
-    return cudaFuncSetAttribute(lz77_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(kSmemTotal));
+    cudaError_t ce = cudaFuncSetAttribute(lz77_parse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(lz77_parse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemTotal));
+    return ce;
 }
 
 cudaError_t launch_parse(const ParseParams &p, int numSMs, cudaStream_t stream)
 {
     if (p.nBlocks == 0) return cudaSuccess;
     const unsigned grid = static_cast<unsigned>(p.nBlocks < static_cast<uint32_t>(numSMs) ? p.nBlocks : numSMs);
-    lz77_parse_kernel<<<grid, kThreads, kSmemTotal, stream>>>(p);
+    if (p.rank16) lz77_parse_kernel<true><<<grid, kThreads, kSmemTotal, stream>>>(p);
+    else lz77_parse_kernel<false><<<grid, kThreads, kSmemTotal, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -65,6 +65,7 @@ constexpr uint32_t kSmemGroup   = (2 * kRingC + 4) * 64 * 4;   // gmax, gown, ha
 constexpr uint32_t kSmemMisc    = 128;          // mbarriers + work-item slot + task counters
 constexpr uint32_t kSmemTotal   = kSmemInput + kSmemTabL + kSmemTabS + kSmemRingH + kSmemRingC + kSmemRingL + kSmemGroup + kSmemMisc;
 static_assert(kSmemTotal <= 232448, "exceeds 227 KB of shared memory per CTA");
+static_assert(kSmemTabS >= 2 * kWindow * 2, "the tag ring (u16 per position, two windows) lives in the spare table");
 static_assert(kSmemTabS + kSmemRingH + kSmemRingC + kSmemRingL >= kBitmapBits / 8, "the detector's bitmap overlays the spare table and the rings");
 
 struct ParseParams {
@@ -81,6 +82,7 @@ struct ParseParams {
     uint32_t *sorted;          // scratch: kSortedCap entries per CTA of the grid (the counting-sorted positions)
     uint32_t keyMask;          // mask on bytes 4..7 for the key hash: 0 (4 B), 0xFF (5 B), 0xFFFF (6 B)
     uint32_t scan;             // bucket entries examined per position, most recent first (<= kIdxCap): the level-scaled depth
+    uint32_t rank16;           // 1: candidates are ranked on their first 16 bytes and only the winner is extended (scan = 4 or 8)
     uint32_t minMatch;         // >= 4
     uint32_t extCap;           // <= kMaxExtCap
     uint32_t lazyDepth;        // 0..2

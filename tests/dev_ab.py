@@ -40,7 +40,9 @@ def one():
             want = oracle.model_block(sample[b * BLOCK:(b + 1) * BLOCK], level)
             got = hs[b, :hc[b]]
             checked += 1
-            if got.shape != want.shape or not (got == want).all(): bad += 1
+            if got.shape != want.shape or not (got == want).all():
+                bad += 1
+                if bad <= 4: print('   differs: level', level, 'block', b, 'counts', hc[b], len(want), flush=True)
     # timing
     out = []
     for level in (3, 6):
