@@ -38,7 +38,8 @@ extern "C" {
 #define B200SP_EINVAL          (-3)   /* bad argument (alignment, block size, level outside 1..12) */
 #define B200SP_ENOMEM          (-4)
 #define B200SP_ECUDA           (-5)   /* CUDA runtime error, see b200sp_error_string() */
-#define B200SP_ETIMEOUT        (-6)   /* completion not seen within the reference's 2 s budget (:107) */
+#define B200SP_ETIMEOUT        (-6)   /* completion not seen within the reference's 2 s budget (:107, :1267-1270) */
+#define B200SP_EVERIFY         (-7)   /* verify-on-return (compressAndVerify, :1238) found a block whose sequences do not replay */
 
 /* One ZSTD_Sequence as the library's own 16-byte type (identical layout to zstd.h's). */
 typedef struct {
@@ -53,6 +54,11 @@ int b200sp_driver_device_count(void);
 
 /* Number of usable (sm_100, enough shared memory) devices; 0 if none; <0 on driver failure. */
 int b200sp_device_count(void);
+
+/* The usable devices' indices, in ascending order (at most `capacity` are written); returns how many there are.
+ * The plugin layer spreads its states over them round-robin, as the reference spreads instances over its
+ * devices (QZSTD_getAndShuffleInstance, /root/reference/src/qatseqprod.c:601-630). */
+int b200sp_usable_devices(int *devices, int capacity);
 
 /* Pays the one-time costs of a device up front (CUDA context, module load, opt-in shared memory), so that
  * the first parsed block does not: the counterpart of the instance start-up the reference does inside
@@ -96,6 +102,21 @@ typedef struct {
 
 int b200sp_parse_host(b200sp_engine *engine, const void *h_src, size_t srcSize, uint32_t blockSize,
                       int level, b200sp_result *result);
+
+/* Host-resident batch, synchronous, result as the array libzstd consumes: dense ZSTD_Sequence[] (16 bytes each) in
+ * h_out, every block ending with its {0, trailing literals, 0} entry - what QZSTD_decLz4s leaves in outSeqs
+ * (/root/reference/src/qatseqprod.c:1013-1091), for every block of the buffer at once.  When h_out is pinned
+ * (cudaHostAlloc / cudaHostRegister) the entries are copied straight into it; otherwise they go through the engine's
+ * pinned staging and a threaded copy.  *nSeqs = entries written; `result` (may be NULL) receives the per-block
+ * counts and offsets (its `packed` is NULL).  B200SP_EINVAL when outCapacity is too small. */
+int b200sp_sequences_host(b200sp_engine *engine, const void *h_src, size_t srcSize, uint32_t blockSize, int level,
+                          b200sp_sequence *h_out, size_t outCapacity, size_t *nSeqs, b200sp_result *result);
+
+/* Verify-on-return, the analogue of the reference's compressAndVerify (/root/reference/src/qatseqprod.c:1238): when
+ * enabled (or QZSTD_VERIFY=1 in the environment at engine creation) every host-path call replays each block's
+ * sequences against its input on the device before returning and fails with B200SP_EVERIFY if any block does not
+ * replay.  Returns the previous setting. */
+int b200sp_engine_set_verify(b200sp_engine *engine, int enable);
 
 /* Host-resident batch of SCATTERED blocks (one pointer and one size <= 128 KiB per block), synchronous:
  * what a dispatcher that coalesces the single-block calls of many threads submits - the analogue of

@@ -102,6 +102,13 @@ def _load():
     l.b200sp_sync.restype = c_int
     l.b200sp_parse_host.argtypes = [c_void_p, c_void_p, c_size_t, c_uint32, c_int, POINTER(_Result)]
     l.b200sp_parse_host.restype = c_int
+    l.b200sp_sequences_host.argtypes = [c_void_p, c_void_p, c_size_t, c_uint32, c_int, c_void_p, c_size_t,
+                                        POINTER(c_size_t), POINTER(_Result)]
+    l.b200sp_sequences_host.restype = c_int
+    l.b200sp_engine_set_verify.argtypes = [c_void_p, c_int]
+    l.b200sp_engine_set_verify.restype = c_int
+    l.b200sp_usable_devices.argtypes = [POINTER(c_int), c_int]
+    l.b200sp_usable_devices.restype = c_int
     l.b200sp_expand.argtypes = [c_void_p, c_size_t, c_void_p]
     l.b200sp_expand.restype = None
     l.b200sp_error_string.restype = c_char_p
@@ -119,6 +126,7 @@ EXPORTED_SYMBOLS = [
     "b200sp_driver_device_count", "b200sp_device_count", "b200sp_warmup", "b200sp_engine_create", "b200sp_engine_destroy",
     "b200sp_engine_device", "b200sp_engine_sm_count", "b200sp_parse_device", "b200sp_sync",
     "b200sp_parse_host", "b200sp_expand", "b200sp_verify_device", "b200sp_error_string", "b200sp_version",
+    "b200sp_sequences_host", "b200sp_engine_set_verify", "b200sp_usable_devices",
 ]
 
 
@@ -180,6 +188,18 @@ class Engine:
         _check(lib.b200sp_parse_host(self._h, h_src, size, block_size, level, ctypes.byref(r)),
                "b200sp_parse_host")
         return r.nBlocks, r.counts, r.offsets, r.packed
+
+    def sequences_host(self, h_src: int, size: int, block_size: int, level: int, h_out: int, out_capacity: int) -> int:
+        """Synchronous host-buffer batch with the result as dense ZSTD_Sequence[] written to h_out (raw pointers;
+        direct DMA when h_out is pinned).  Returns the number of entries."""
+        n = c_size_t(0)
+        _check(lib.b200sp_sequences_host(self._h, h_src, size, block_size, level, h_out, out_capacity,
+                                         ctypes.byref(n), None), "b200sp_sequences_host")
+        return n.value
+
+    def set_verify(self, enable: bool) -> bool:
+        """Verify-on-return (the reference's compressAndVerify): replay every block on the device before returning."""
+        return bool(lib.b200sp_engine_set_verify(self._h, 1 if enable else 0))
 
     def parse_host_numpy(self, data, block_size: int = BLOCK_MAX, level: int = 3):
         """Convenience for tests/tools: bytes-like in, (counts, offsets, sequences[n,4] u32) numpy out."""

@@ -144,6 +144,19 @@ __device__ __forceinline__ uint32_t pop_task(uint32_t ctrAddr, uint32_t lane)
     return __shfl_sync(0xFFFFFFFFu, id, 0);
 }
 
+// Bounded wait for a hand-off word between the parse / emit warps of one CTA (written a few hundred cycles after
+// it is first polled): a word that never arrives would otherwise hang the device until the watchdog.  On overrun
+// the error flag is raised (the host reports B200SP_ECUDA) and the warp carries on with whatever it reads.
+constexpr uint32_t kSpinLimit = 1u << 22;      // x B200SP_SPIN_NS = ~0.4 s
+__device__ __forceinline__ void spin_until(uint32_t addr, uint32_t expect, unsigned int *errorFlag)
+{
+    uint32_t spins = 0;
+    while (lds32(addr) != expect) {
+        __nanosleep(B200SP_SPIN_NS);
+        if (++spins > kSpinLimit) { if (errorFlag) atomicExch(errorFlag, 1u); break; }
+    }
+}
+
 // XOR swizzle of the ring words: conflict-free by group (a warp writes its group) and by lane (a parse lane
 // reads the same local position in 32 groups).
 __device__ __forceinline__ uint32_t ring_byte(uint32_t group, uint32_t lane)   // byte offset of a 32-bit ring word
@@ -574,7 +587,7 @@ __device__ __forceinline__ uint32_t eval_step(uint32_t pkRow, uint32_t group, ui
 }
 
 __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint32_t half, uint32_t lane,
-                                              uint32_t minMatch, uint32_t lazyDepth)
+                                              uint32_t minMatch, uint32_t lazyDepth, unsigned int *errorFlag)
 {
     // Lane j owns group half * kHalf + j of the window.  The two halves of a window are handled by two warps in
     // the same stage: where the parse enters a half is published by the warp of the half before it (the second
@@ -652,7 +665,7 @@ __device__ __forceinline__ void stage_entries(const Shared &S, uint32_t w, uint3
         if (!__any_sync(0xFFFFFFFFu, changed)) {
             if (known) break;
             // converged on a guessed entry of the half: wait for the real one (warp-uniform spin)
-            while (lds32(S.curTag) != expect) __nanosleep(B200SP_SPIN_NS);
+            spin_until(S.curTag, expect, errorFlag);
             __threadfence_block();
             cursor = lds32(S.curVal);
             known = true;
@@ -691,7 +704,7 @@ struct EmitCarry {           // uniform across the warp, carried from window to 
 // The two halves of a window are emitted by two warps in the same stage.  The carry (anchor, previous offset,
 // sequences written) travels through shared memory like the entry cursor: the first half's warp publishes it
 // right after its scans, so the second half's warp - which has done its counting walk meanwhile - waits little.
-__device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t half, uint32_t lane, EmitCarry &ec, uint4 *out)
+__device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t half, uint32_t lane, EmitCarry &ec, uint4 *out, unsigned int *errorFlag)
 {
     const uint32_t base = w * kWindow, group = half * kHalf + lane;
     const bool act = lane < kHalf;
@@ -724,7 +737,7 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
         const uint32_t expect = 2u * w + half;
         if (expect == 0u) { ec.anchor = 0u; ec.prevOff = 0u; ec.nOut = 0u; }
         else {
-            while (lds32(S.ecTag) != expect) __nanosleep(B200SP_SPIN_NS);
+            spin_until(S.ecTag, expect, errorFlag);
             __threadfence_block();
             ec.anchor = lds32(S.ecVal); ec.prevOff = lds32(S.ecVal + 4u); ec.nOut = lds32(S.ecVal + 8u);
         }
@@ -790,7 +803,7 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
     // A continuation is added to a sequence an earlier lane wrote - for the second half possibly a lane of the
     // first half's warp, which must have stored it before (its stores of earlier windows are a stage old).
     if (half == 1u) {
-        while (lds32(S.emTag) != w + 1u) __nanosleep(B200SP_SPIN_NS);
+        spin_until(S.emTag, w + 1u, errorFlag);
         __threadfence();
     }
     if (headAdd) atomicAdd(&out[firstIdx - 1].z, headAdd);   // continuation of an earlier lane's sequence
@@ -990,9 +1003,9 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 // spare warp
             } else if (role <= 4u) {
                 if (role == 3u && lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, kEhWarps);   // next stage's queue (nobody touches it now)
-                if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, role - 3u, lane, P.minMatch, P.lazyDepth);
+                if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, role - 3u, lane, P.minMatch, P.lazyDepth, P.errorFlag);
             } else {
-                if (t >= 4) stage_emit(S, t - 4, role - 5u, lane, ec, out);
+                if (t >= 4) stage_emit(S, t - 4, role - 5u, lane, ec, out, P.errorFlag);
             }
 #ifdef B200SP_ROLE_PROFILE
             busy += clock64() - c0;

@@ -79,6 +79,7 @@ struct ParseParams {
     uint64_t seqStride;
     uint32_t *counts;          // entries written per block (incl. the final literals entry)
     unsigned int *workCounter; // zeroed before launch; dynamic block scheduler
+    unsigned int *errorFlag;   // optional: set to 1 when a bounded in-kernel wait ran out (never cleared by the kernel)
     uint32_t *sorted;          // scratch: kSortedCap entries per CTA of the grid (the counting-sorted positions)
     uint32_t keyMask;          // mask on bytes 4..7 for the key hash: 0 (4 B), 0xFF (5 B), 0xFFFF (6 B)
     uint32_t scan;             // bucket entries examined per position, most recent first (<= kIdxCap): the level-scaled depth

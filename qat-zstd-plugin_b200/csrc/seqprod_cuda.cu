@@ -13,6 +13,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <thread>
+#include <vector>
 
 namespace {
 
@@ -30,6 +33,84 @@ int fail(int code, const char *what, cudaError_t ce = cudaSuccess)
         cudaError_t ce_ = (expr);                                     \
         if (ce_ != cudaSuccess) return fail(B200SP_ECUDA, what, ce_); \
     } while (0)
+
+// Every C-ABI entry point runs on its engine's device and puts the caller's current device back on the way out:
+// a host process that uses CUDA on another GPU must not find its thread switched.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t enter(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); prev = -1; }
+        if (prev == dev) return cudaSuccess;
+        const cudaError_t ce = cudaSetDevice(dev);
+        switched = ce == cudaSuccess;
+        return ce;
+    }
+    ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+};
+
+// Completion wait with the reference's budget (QZSTD timeout, /root/reference/src/qatseqprod.c:107, :1099-1104,
+// :1267-1270: 2 s, then ERROR): poll instead of blocking forever.
+constexpr double kTimeoutSeconds = 2.0;
+
+double now_seconds()
+{
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return static_cast<double>(t.tv_sec) + 1e-9 * static_cast<double>(t.tv_nsec);
+}
+
+// 0 = done, 1 = timed out, otherwise the CUDA error
+int wait_event(cudaEvent_t ev, cudaError_t *ce)
+{
+    const double deadline = now_seconds() + kTimeoutSeconds;
+    for (unsigned spins = 0;; spins++) {
+        const cudaError_t q = cudaEventQuery(ev);
+        if (q == cudaSuccess) return 0;
+        if (q != cudaErrorNotReady) { *ce = q; return 2; }
+        if (spins > 2000) {         // the first ~2000 polls spin (short waits stay short), then yield
+            if (now_seconds() > deadline) return 1;
+            timespec ts = {0, 20000};
+            nanosleep(&ts, nullptr);
+        }
+    }
+}
+
+int wait_stream(cudaStream_t st, cudaError_t *ce)
+{
+    const double deadline = now_seconds() + kTimeoutSeconds;
+    for (unsigned spins = 0;; spins++) {
+        const cudaError_t q = cudaStreamQuery(st);
+        if (q == cudaSuccess) return 0;
+        if (q != cudaErrorNotReady) { *ce = q; return 2; }
+        if (spins > 2000) {
+            if (now_seconds() > deadline) return 1;
+            timespec ts = {0, 20000};
+            nanosleep(&ts, nullptr);
+        }
+    }
+}
+
+// memcpy of a large range by a few threads (results landing in pageable caller memory)
+void parallel_copy(void *dst, const void *src, size_t bytes)
+{
+    constexpr size_t kPerThread = 4u << 20;
+    unsigned n = static_cast<unsigned>(bytes / kPerThread);
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (n > 8) n = 8;
+    if (hw && n > hw) n = hw;
+    if (n <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = (bytes / n + 63) & ~static_cast<size_t>(63);
+    for (unsigned i = 0; i < n; i++) {
+        const size_t off = static_cast<size_t>(i) * per;
+        if (off >= bytes) break;
+        const size_t len = off + per < bytes ? per : bytes - off;
+        th.emplace_back([=] { memcpy(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, len); });
+    }
+    for (auto &t : th) t.join();
+}
 
 bool device_usable(int dev)
 {
@@ -81,6 +162,27 @@ __global__ void __launch_bounds__(kPostThreads) pack_kernel(const uint4 *__restr
                    (static_cast<unsigned long long>(q.z) << 35);
         }
     }
+}
+
+// The same gather without repacking: dense ZSTD_Sequence[] (16 bytes each), the array the plugin API hands to libzstd.
+__global__ void __launch_bounds__(kPostThreads) dense_kernel(const uint4 *__restrict__ seqs, uint64_t seqStride,
+                             const uint32_t *__restrict__ counts,
+                             const unsigned long long *__restrict__ offsets, uint32_t nBlocks,
+                             uint4 *__restrict__ dense)
+{
+    for (uint32_t b = blockIdx.x; b < nBlocks; b += gridDim.x) {
+        const uint4 *s = seqs + static_cast<uint64_t>(b) * seqStride;
+        uint4 *o = dense + offsets[b];
+        const uint32_t c = counts[b];
+        for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) o[i] = s[i];
+    }
+}
+
+__global__ void count_bad_kernel(const uint32_t *__restrict__ bad, uint32_t nBlocks, uint32_t *__restrict__ total)
+{
+    uint32_t n = 0;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nBlocks; b += gridDim.x * blockDim.x) n += bad[b] != 0u;
+    if (n) atomicAdd(total, n);
 }
 
 // ---- on-device verification: one warp replays one block ------------------------------------
@@ -183,8 +285,14 @@ struct b200sp_engine {
     uint32_t *d_counts;  size_t d_countsCap;
     unsigned long long *d_offsets; size_t d_offsetsCap;
     unsigned long long *d_packed; size_t d_packedCap;   // entries
-    uint8_t *h_stage;    size_t h_stageCap;     // pinned staging for pageable inputs
+    uint8_t *h_stage;    size_t h_stageCap;     // pinned staging for pageable inputs of the host path
+    uint8_t *h_slots;    size_t h_slotsCap;     // pinned staging of the scattered-block path (its own buffer: the address handed out stays valid)
     uint32_t stageSlots;                        // slots reserved by b200sp_stage_reserve (scattered-block path)
+    uint32_t *d_bad;     size_t d_badCap;       // verify-on-return: per-block verdicts + [0] of d_badTotal
+    uint32_t *d_badTotal;
+    uint32_t *h_badTotal;                       // pinned
+    uint32_t *h_flag;                           // pinned copy of the kernel's error flag
+    int verify;                                 // QZSTD_VERIFY / b200sp_engine_set_verify: replay every block on the device before returning
     uint32_t *h_counts;  size_t h_countsCap;
     unsigned long long *h_offsets; size_t h_offsetsCap;  // chunk-local (pinned)
     unsigned long long *h_goffsets; size_t h_goffsetsCap; // global, handed to the caller
@@ -213,6 +321,17 @@ int b200sp_device_count(void)
     return usable;
 }
 
+int b200sp_usable_devices(int *devices, int capacity)
+{
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess) { (void)cudaGetLastError(); return fail(B200SP_ENODEVICE, "cudaGetDeviceCount", ce); }
+    int usable = 0;
+    for (int d = 0; d < n; d++)
+        if (device_usable(d)) { if (devices && usable < capacity) devices[usable] = d; usable++; }
+    return usable;
+}
+
 int b200sp_warmup(int device)
 {
     int n = 0;
@@ -220,7 +339,8 @@ int b200sp_warmup(int device)
     if (ce != cudaSuccess || n == 0) { (void)cudaGetLastError(); return fail(B200SP_ENODEVICE, "no CUDA device", ce); }
     if (device < 0 || device >= n) return fail(B200SP_EINVAL, "warmup: device index out of range");
     if (!device_usable(device)) return fail(B200SP_EUNSUPPORTED, "device is not sm_100 with 227 KB shared memory per CTA");
-    CU_TRY(cudaSetDevice(device), "cudaSetDevice");
+    DeviceGuard guard;
+    CU_TRY(guard.enter(device), "cudaSetDevice");
     CU_TRY(cudaFree(nullptr), "context creation");
     CU_TRY(b200sp::configure_kernels(), "cudaFuncSetAttribute(max dynamic smem)");      // loads the module
     return B200SP_OK;
@@ -235,11 +355,13 @@ int b200sp_engine_create(int device, b200sp_engine **out)
     if (ce != cudaSuccess || n == 0) { (void)cudaGetLastError(); return fail(B200SP_ENODEVICE, "no CUDA device", ce); }
     if (device < 0 || device >= n) return fail(B200SP_EINVAL, "engine_create: device index out of range");
     if (!device_usable(device)) return fail(B200SP_EUNSUPPORTED, "device is not sm_100 with 227 KB shared memory per CTA");
-    CU_TRY(cudaSetDevice(device), "cudaSetDevice");
+    DeviceGuard guard;
+    CU_TRY(guard.enter(device), "cudaSetDevice");
     CU_TRY(b200sp::configure_kernels(), "cudaFuncSetAttribute(max dynamic smem)");
     b200sp_engine *e = static_cast<b200sp_engine *>(calloc(1, sizeof(b200sp_engine)));
     if (!e) return fail(B200SP_ENOMEM, "engine_create: out of host memory");
     e->device = device;
+    { const char *v = getenv("QZSTD_VERIFY"); e->verify = (v && *v && *v != '0') ? 1 : 0; }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     e->numSMs = prop.multiProcessorCount;
@@ -261,6 +383,8 @@ int b200sp_engine_create(int device, b200sp_engine **out)
     if (ce == cudaSuccess) ce = cudaMalloc(&e->d_work, 256);
     if (ce == cudaSuccess) ce = cudaMemset(e->d_work, 0, 256);
     if (ce == cudaSuccess) ce = cudaMalloc(&e->d_chunkWork, kMaxChunks * sizeof(unsigned int));
+    if (ce == cudaSuccess) ce = cudaMallocHost(&e->h_flag, sizeof(uint32_t));
+    if (ce == cudaSuccess) *e->h_flag = 0;
     if (ce != cudaSuccess) { b200sp_engine_destroy(e); return fail(B200SP_ECUDA, "engine_create", ce); }
     *out = e;
     return B200SP_OK;
@@ -269,7 +393,8 @@ int b200sp_engine_create(int device, b200sp_engine **out)
 void b200sp_engine_destroy(b200sp_engine *e)
 {
     if (!e) return;
-    cudaSetDevice(e->device);
+    DeviceGuard guard;
+    guard.enter(e->device);
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
     if (e->sIn) cudaStreamDestroy(e->sIn);
     if (e->sOut) { cudaStreamSynchronize(e->sOut); cudaStreamDestroy(e->sOut); }
@@ -285,7 +410,7 @@ void b200sp_engine_destroy(b200sp_engine *e)
     free(e->h_goffsets);
     cudaFree(e->d_work); cudaFree(e->d_src); cudaFree(e->d_seqs); cudaFree(e->d_counts);
     cudaFree(e->d_offsets); cudaFree(e->d_packed);
-    cudaFreeHost(e->h_stage); cudaFreeHost(e->h_counts); cudaFreeHost(e->h_offsets); cudaFreeHost(e->h_packed);
+    cudaFreeHost(e->h_flag); cudaFreeHost(e->h_stage); cudaFreeHost(e->h_slots); cudaFreeHost(e->h_badTotal); cudaFree(e->d_bad); cudaFree(e->d_badTotal); cudaFreeHost(e->h_counts); cudaFreeHost(e->h_offsets); cudaFreeHost(e->h_packed);
     free(e);
 }
 
@@ -319,7 +444,8 @@ static int launch_batch(b200sp_engine *e, const void *d_src, uint64_t totalSize,
     if (rc) return rc;
     if (nBlocks == 0) return B200SP_OK;
     if (!d_seqs || !d_counts) return fail(B200SP_EINVAL, "null output");
-    CU_TRY(cudaSetDevice(e->device), "cudaSetDevice");
+    DeviceGuard guard;
+    CU_TRY(guard.enter(e->device), "cudaSetDevice");
     {
         const uint32_t grid = nBlocks < static_cast<uint32_t>(e->numSMs) ? nBlocks : static_cast<uint32_t>(e->numSMs);
         const size_t want = static_cast<size_t>(grid) * b200sp::kSortedCap;
@@ -341,6 +467,7 @@ static int launch_batch(b200sp_engine *e, const void *d_src, uint64_t totalSize,
     p.seqStride = seqStride;
     p.counts = d_counts;
     p.workCounter = workCounter;
+    p.errorFlag = e->d_work + 48;                  // one word of the 256-byte counter block, checked by the host paths
     // developer profiling: B200SP_ROLE_PROFILE=1 accumulates per-role busy cycles in d_work[8..]
     static const bool roleProfile = getenv("B200SP_ROLE_PROFILE") != nullptr;
     p.roleCycles = roleProfile ? reinterpret_cast<unsigned long long *>(e->d_work) + 1 : nullptr;
@@ -368,7 +495,8 @@ int b200sp_verify_device(b200sp_engine *e, const void *d_src, uint64_t totalSize
     if (nBlocks == 0) return B200SP_OK;
     if (!d_src || !d_seqs || !d_counts || !d_bad) return fail(B200SP_EINVAL, "null argument");
     cudaStream_t st = cudaStream ? static_cast<cudaStream_t>(cudaStream) : e->stream;
-    CU_TRY(cudaSetDevice(e->device), "cudaSetDevice");
+    DeviceGuard guard;
+    CU_TRY(guard.enter(e->device), "cudaSetDevice");
     const unsigned threads = 128, warpsPerCta = threads / 32;
     unsigned grid = (nBlocks + warpsPerCta - 1) / warpsPerCta;
     if (grid > static_cast<unsigned>(e->numSMs) * 16u) grid = e->numSMs * 16u;
@@ -393,20 +521,47 @@ int b200sp_debug_role_cycles(b200sp_engine *e, unsigned long long *out6)
 int b200sp_sync(b200sp_engine *e)
 {
     if (!e) return fail(B200SP_EINVAL, "null engine");
-    CU_TRY(cudaStreamSynchronize(e->stream), "cudaStreamSynchronize");
+    DeviceGuard guard;
+    CU_TRY(guard.enter(e->device), "cudaSetDevice");
+    cudaError_t wce = cudaSuccess;
+    const int w = wait_stream(e->stream, &wce);
+    if (w == 1) return fail(B200SP_ETIMEOUT, "no completion within 2 s");
+    if (w) return fail(B200SP_ECUDA, "cudaStreamQuery", wce);
     return B200SP_OK;
 }
 
-int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint32_t blockSize, int level,
-                      b200sp_result *res)
+// Drains the engine's streams after a failure part-way through a pipelined call, so that nothing is still writing
+// into (or reading from) the engine's buffers when the caller sees the error.
+static void quiesce(b200sp_engine *e)
 {
-    if (!e || !res) return fail(B200SP_EINVAL, "null engine/result");
-    memset(res, 0, sizeof *res);
+    cudaStreamSynchronize(e->sIn);
+    cudaStreamSynchronize(e->sParse[0]);
+    cudaStreamSynchronize(e->sParse[1]);
+    cudaStreamSynchronize(e->sPost);
+    cudaStreamSynchronize(e->sOut);
+    (void)cudaGetLastError();
+}
+
+#define CU_TRY_Q(expr, what)                                                         \
+    do {                                                                             \
+        cudaError_t ce_ = (expr);                                                    \
+        if (ce_ != cudaSuccess) { quiesce(e); return fail(B200SP_ECUDA, what, ce_); } \
+    } while (0)
+
+// The pipelined host path.  out16 == nullptr: results come back in the 8-byte wire format (res);
+// out16 != nullptr: dense ZSTD_Sequence[] straight into the caller's array (direct DMA when it is pinned,
+// through pinned staging and a threaded copy otherwise), *nOut = entries written.
+static int host_pipeline(b200sp_engine *e, const void *h_src, size_t srcSize, uint32_t blockSize, int level,
+                         b200sp_result *res, b200sp_sequence *out16, size_t outCap, size_t *nOut)
+{
     if (blockSize == 0 || blockSize > B200SP_BLOCK_MAX) return fail(B200SP_EINVAL, "blockSize must be 1..131072");
     if (level < 1 || level > 12) return fail(B200SP_EINVAL, "compression level outside 1..12");
     if (srcSize == 0) return B200SP_OK;
     if (!h_src) return fail(B200SP_EINVAL, "null source");
-    CU_TRY(cudaSetDevice(e->device), "cudaSetDevice");
+    DeviceGuard guard;
+    CU_TRY(guard.enter(e->device), "cudaSetDevice");
+    const bool dense = out16 != nullptr;
+    const size_t entryBytes = dense ? 16 : 8;
 
     // blocks are laid out on the device at a 16-byte-aligned stride
     const uint64_t stride = (static_cast<uint64_t>(blockSize) + 15u) & ~15ull;
@@ -437,7 +592,7 @@ int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint3
         CU_TRY(grow_dev(e->d_seqs, e->d_seqsCap, nBlocks * seqStride), "cudaMalloc(seqs)");
         CU_TRY(grow_dev(e->d_counts, e->d_countsCap, nBlocks), "cudaMalloc(counts)");
         CU_TRY(grow_dev(e->d_offsets, e->d_offsetsCap, nBlocks + kMaxChunks), "cudaMalloc(offsets)");
-        CU_TRY(grow_dev(e->d_packed, e->d_packedCap, nBlocks * perBlockWorst), "cudaMalloc(packed)");
+        CU_TRY(grow_dev(e->d_packed, e->d_packedCap, nBlocks * perBlockWorst * (dense ? 2 : 1)), "cudaMalloc(packed)");
         CU_TRY(grow_host(e->h_counts, e->h_countsCap, nBlocks), "cudaMallocHost(counts)");
         CU_TRY(grow_host(e->h_offsets, e->h_offsetsCap, nBlocks + kMaxChunks), "cudaMallocHost(offsets)");
         if (e->h_goffsetsCap < nBlocks + 1) {
@@ -446,19 +601,33 @@ int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint3
             if (!e->h_goffsets) { e->h_goffsetsCap = 0; return fail(B200SP_ENOMEM, "out of host memory"); }
             e->h_goffsetsCap = nBlocks + 1 + nBlocks / 4;
         }
-        // typical text yields one entry per 10-20 input bytes; grown on demand below
-        CU_TRY(grow_host(e->h_packed, e->h_packedCap, srcSize / 12 + 4 * nBlocks + 1024), "cudaMallocHost(packed)");
+        if (e->verify) {
+            CU_TRY(grow_dev(e->d_bad, e->d_badCap, nBlocks), "cudaMalloc(verify)");
+            if (!e->d_badTotal) CU_TRY(cudaMalloc(&e->d_badTotal, sizeof(uint32_t)), "cudaMalloc(verify total)");
+            if (!e->h_badTotal) CU_TRY(cudaMallocHost(&e->h_badTotal, sizeof(uint32_t)), "cudaMallocHost(verify total)");
+            CU_TRY(cudaMemsetAsync(e->d_badTotal, 0, sizeof(uint32_t), e->sPost), "memset(verify total)");
+        }
     }
 
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, h_src) == cudaSuccess &&
                         (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
     (void)cudaGetLastError();
+    bool outPinned = false;
+    if (dense) {
+        outPinned = cudaPointerGetAttributes(&attr, out16) == cudaSuccess &&
+                    (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
+        (void)cudaGetLastError();
+    }
+    // staging for results that cannot be copied straight to their destination: the wire format always lands in the
+    // engine's pinned array; dense output only when the caller's array is pageable.
+    // typical text yields one entry per 10-20 input bytes; grown on demand below
+    if (!dense || !outPinned)
+        CU_TRY(grow_host(e->h_packed, e->h_packedCap, (srcSize / 12 + 4 * nBlocks + 1024) * (dense ? 2 : 1)), "cudaMallocHost(packed)");
     const uint8_t *hs = static_cast<const uint8_t *>(h_src);
     if (!pinned) CU_TRY(grow_host(e->h_stage, e->h_stageCap, srcSize), "cudaMallocHost(stage)");
 
-    // ---- enqueue: per chunk H2D on the copy-in stream, then parse + scan + pack + small D2H on the
-    // compute stream behind an event
+    // ---- enqueue: per chunk H2D on the copy-in stream, then parse (+ verify) + scan + pack + small D2H behind events
     for (int k = 0; k < nChunks; k++) {
         const size_t b0 = chunkStart[k], b1 = chunkStart[k + 1], nb = b1 - b0;
         const size_t byte0 = b0 * blockSize, byte1 = b1 * blockSize < srcSize ? b1 * blockSize : srcSize;
@@ -470,15 +639,15 @@ int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint3
         }
         uint8_t *dsrc = e->d_src + b0 * stride;
         if (stride == blockSize) {
-            CU_TRY(cudaMemcpyAsync(dsrc, hsrc, byte1 - byte0, cudaMemcpyHostToDevice, e->sIn), "H2D");
+            CU_TRY_Q(cudaMemcpyAsync(dsrc, hsrc, byte1 - byte0, cudaMemcpyHostToDevice, e->sIn), "H2D");
         } else {
             const size_t full = (byte1 - byte0) / blockSize, rem = (byte1 - byte0) % blockSize;
-            if (full) CU_TRY(cudaMemcpy2DAsync(dsrc, stride, hsrc, blockSize, blockSize, full, cudaMemcpyHostToDevice, e->sIn), "H2D 2D");
-            if (rem) CU_TRY(cudaMemcpyAsync(dsrc + full * stride, hsrc + full * blockSize, rem, cudaMemcpyHostToDevice, e->sIn), "H2D tail");
+            if (full) CU_TRY_Q(cudaMemcpy2DAsync(dsrc, stride, hsrc, blockSize, blockSize, full, cudaMemcpyHostToDevice, e->sIn), "H2D 2D");
+            if (rem) CU_TRY_Q(cudaMemcpyAsync(dsrc + full * stride, hsrc + full * blockSize, rem, cudaMemcpyHostToDevice, e->sIn), "H2D tail");
         }
-        CU_TRY(cudaEventRecord(e->evIn[k], e->sIn), "event record");
+        CU_TRY_Q(cudaEventRecord(e->evIn[k], e->sIn), "event record");
         cudaStream_t sp = e->sParse[k & 1];
-        CU_TRY(cudaStreamWaitEvent(sp, e->evIn[k], 0), "stream wait");
+        CU_TRY_Q(cudaStreamWaitEvent(sp, e->evIn[k], 0), "stream wait");
 
         // sizes in the strided layout: the last block of the chunk holds what is left of the input
         const uint64_t lastBytes = (byte1 - byte0) - (nb - 1) * static_cast<size_t>(blockSize);
@@ -488,50 +657,115 @@ int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint3
         unsigned long long *doffs = e->d_offsets + b0 + k;
         int rc = launch_batch(e, dsrc, totalStrided, blockSize, stride, nullptr, static_cast<uint32_t>(nb), level,
                               reinterpret_cast<b200sp_sequence *>(dseqs), seqStride, dcounts, sp, e->d_chunkWork + k, 1 + (k & 1));
-        if (rc) return rc;
-        CU_TRY(cudaEventRecord(e->evParsed[k], sp), "event record");
-        CU_TRY(cudaStreamWaitEvent(e->sPost, e->evParsed[k], 0), "stream wait");
+        if (rc) { quiesce(e); return rc; }
+        CU_TRY_Q(cudaEventRecord(e->evParsed[k], sp), "event record");
+        CU_TRY_Q(cudaStreamWaitEvent(e->sPost, e->evParsed[k], 0), "stream wait");
+        if (e->verify) {        // compress-and-verify (/root/reference/src/qatseqprod.c:1238): replay before anything is returned
+            const unsigned vthreads = 128, warpsPerCta = vthreads / 32;
+            unsigned vgrid = static_cast<unsigned>((nb + warpsPerCta - 1) / warpsPerCta);
+            if (vgrid > static_cast<unsigned>(e->numSMs) * 16u) vgrid = e->numSMs * 16u;
+            verify_kernel<<<vgrid, vthreads, 0, e->sPost>>>(dsrc, stride, totalStrided, blockSize, nullptr, static_cast<uint32_t>(nb),
+                                                           dseqs, seqStride, dcounts, e->d_bad + b0);
+            count_bad_kernel<<<8, 128, 0, e->sPost>>>(e->d_bad + b0, static_cast<uint32_t>(nb), e->d_badTotal);
+            CU_TRY_Q(cudaGetLastError(), "launch verify_kernel");
+        }
         scan_counts_kernel<<<1, 32, 0, e->sPost>>>(dcounts, static_cast<uint32_t>(nb), doffs);
-        CU_TRY(cudaGetLastError(), "launch scan_counts_kernel");
-        pack_kernel<<<e->numSMs * 2, kPostThreads, 0, e->sPost>>>(dseqs, seqStride, dcounts, doffs, static_cast<uint32_t>(nb),
-                                                                 e->d_packed + b0 * perBlockWorst);
-        CU_TRY(cudaGetLastError(), "launch pack_kernel");
-        CU_TRY(cudaMemcpyAsync(e->h_counts + b0, dcounts, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->sPost), "D2H counts");
-        CU_TRY(cudaMemcpyAsync(e->h_offsets + b0 + k, doffs, (nb + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->sPost), "D2H offsets");
-        CU_TRY(cudaEventRecord(e->evDone[k], e->sPost), "event record");
+        CU_TRY_Q(cudaGetLastError(), "launch scan_counts_kernel");
+        if (dense)
+            dense_kernel<<<e->numSMs * 2, kPostThreads, 0, e->sPost>>>(dseqs, seqStride, dcounts, doffs, static_cast<uint32_t>(nb),
+                                                                      reinterpret_cast<uint4 *>(e->d_packed) + b0 * perBlockWorst);
+        else
+            pack_kernel<<<e->numSMs * 2, kPostThreads, 0, e->sPost>>>(dseqs, seqStride, dcounts, doffs, static_cast<uint32_t>(nb),
+                                                                     e->d_packed + b0 * perBlockWorst);
+        CU_TRY_Q(cudaGetLastError(), "launch pack_kernel");
+        CU_TRY_Q(cudaMemcpyAsync(e->h_counts + b0, dcounts, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->sPost), "D2H counts");
+        CU_TRY_Q(cudaMemcpyAsync(e->h_offsets + b0 + k, doffs, (nb + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->sPost), "D2H offsets");
+        CU_TRY_Q(cudaEventRecord(e->evDone[k], e->sPost), "event record");
     }
+    if (e->verify) CU_TRY_Q(cudaMemcpyAsync(e->h_badTotal, e->d_badTotal, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->sPost), "D2H verify total");
+    CU_TRY_Q(cudaMemcpyAsync(e->h_flag, e->d_work + 48, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->sPost), "D2H error flag");
 
-    // ---- drain: as each chunk completes, fetch exactly its packed entries on the copy-out stream
+    // ---- drain: as each chunk completes, fetch exactly its entries on the copy-out stream
     size_t hostPos = 0;
     for (int k = 0; k < nChunks; k++) {
         const size_t b0 = chunkStart[k], nb = chunkStart[k + 1] - b0;
-        CU_TRY(cudaEventSynchronize(e->evDone[k]), "wait chunk");
+        cudaError_t wce = cudaSuccess;
+        const int w = wait_event(e->evDone[k], &wce);
+        if (w == 1) { return fail(B200SP_ETIMEOUT, "no completion within 2 s"); }      // like the reference: give up, report an error
+        if (w) { quiesce(e); return fail(B200SP_ECUDA, "wait chunk", wce); }
         const unsigned long long *lo = e->h_offsets + b0 + k;
         const size_t total = static_cast<size_t>(lo[nb]);
-        if (hostPos + total > e->h_packedCap) {
-            // rare: denser than one entry per 12 bytes. Finish the copies in flight, move to a bigger buffer.
-            CU_TRY(cudaStreamSynchronize(e->sOut), "sync before grow");
-            unsigned long long *bigger = nullptr;
-            const size_t cap = (hostPos + total) * 2 + 1024;
-            CU_TRY(cudaMallocHost(&bigger, cap * sizeof(unsigned long long)), "cudaMallocHost(packed grow)");
-            memcpy(bigger, e->h_packed, hostPos * sizeof(unsigned long long));
-            cudaFreeHost(e->h_packed);
-            e->h_packed = bigger;
-            e->h_packedCap = cap;
+        uint8_t *dst;
+        if (dense && outPinned) {
+            if (hostPos + total > outCap) { quiesce(e); return fail(B200SP_EINVAL, "sequence array too small"); }
+            dst = reinterpret_cast<uint8_t *>(out16 + hostPos);
+        } else {
+            if ((hostPos + total) * entryBytes > e->h_packedCap * 8) {
+                // rare: denser than one entry per 12 bytes. Finish the copies in flight, move to a bigger buffer.
+                CU_TRY_Q(cudaStreamSynchronize(e->sOut), "sync before grow");
+                unsigned long long *bigger = nullptr;
+                const size_t cap = ((hostPos + total) * 2 + 1024) * (dense ? 2 : 1);
+                CU_TRY_Q(cudaMallocHost(&bigger, cap * sizeof(unsigned long long)), "cudaMallocHost(packed grow)");
+                memcpy(bigger, e->h_packed, hostPos * entryBytes);
+                cudaFreeHost(e->h_packed);
+                e->h_packed = bigger;
+                e->h_packedCap = cap;
+            }
+            dst = reinterpret_cast<uint8_t *>(e->h_packed) + hostPos * entryBytes;
         }
-        CU_TRY(cudaMemcpyAsync(e->h_packed + hostPos, e->d_packed + b0 * perBlockWorst, total * sizeof(unsigned long long),
-                               cudaMemcpyDeviceToHost, e->sOut), "D2H packed");
+        const uint8_t *dsrcEntries = reinterpret_cast<const uint8_t *>(e->d_packed) + b0 * perBlockWorst * entryBytes;
+        CU_TRY_Q(cudaMemcpyAsync(dst, dsrcEntries, total * entryBytes, cudaMemcpyDeviceToHost, e->sOut), "D2H entries");
         for (size_t i = 0; i < nb; i++) e->h_goffsets[b0 + i] = hostPos + lo[i];
         hostPos += total;
     }
     e->h_goffsets[nBlocks] = hostPos;
-    CU_TRY(cudaStreamSynchronize(e->sOut), "sync after D2H");
+    {
+        cudaError_t wce = cudaSuccess;
+        int w = wait_stream(e->sOut, &wce);
+        if (!w) w = wait_stream(e->sPost, &wce);
+        if (w == 1) return fail(B200SP_ETIMEOUT, "no completion within 2 s");
+        if (w) { quiesce(e); return fail(B200SP_ECUDA, "sync after D2H", wce); }
+    }
+    if (*e->h_flag != 0) return fail(B200SP_ECUDA, "the parser gave up waiting for an internal hand-off");
+    if (e->verify && *e->h_badTotal != 0) return fail(B200SP_EVERIFY, "on-device verification rejected a block");
+    if (dense && !outPinned) {
+        if (hostPos > outCap) return fail(B200SP_EINVAL, "sequence array too small");
+        parallel_copy(out16, e->h_packed, hostPos * 16);
+    }
+    if (nOut) *nOut = hostPos;
 
     res->nBlocks = static_cast<uint32_t>(nBlocks);
     res->counts = e->h_counts;
     res->offsets = reinterpret_cast<const uint64_t *>(e->h_goffsets);
-    res->packed = reinterpret_cast<const uint64_t *>(e->h_packed);
+    res->packed = dense ? nullptr : reinterpret_cast<const uint64_t *>(e->h_packed);
     return B200SP_OK;
+}
+
+int b200sp_parse_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint32_t blockSize, int level,
+                      b200sp_result *res)
+{
+    if (!e || !res) return fail(B200SP_EINVAL, "null engine/result");
+    memset(res, 0, sizeof *res);
+    return host_pipeline(e, h_src, srcSize, blockSize, level, res, nullptr, 0, nullptr);
+}
+
+int b200sp_sequences_host(b200sp_engine *e, const void *h_src, size_t srcSize, uint32_t blockSize, int level,
+                          b200sp_sequence *h_out, size_t outCapacity, size_t *nSeqs, b200sp_result *res)
+{
+    b200sp_result local;
+    if (!e || !h_out || !nSeqs) return fail(B200SP_EINVAL, "null engine/output");
+    *nSeqs = 0;
+    if (!res) res = &local;
+    memset(res, 0, sizeof *res);
+    return host_pipeline(e, h_src, srcSize, blockSize, level, res, h_out, outCapacity, nSeqs);
+}
+
+int b200sp_engine_set_verify(b200sp_engine *e, int enable)
+{
+    if (!e) return fail(B200SP_EINVAL, "null engine");
+    const int before = e->verify;
+    e->verify = enable ? 1 : 0;
+    return before;
 }
 
 // Staging layout of the scattered-block path: [sizes (u32 per slot, padded to 16 B)] [slot 0] [slot 1] ... at a
@@ -544,15 +778,16 @@ static size_t staged_sizes_bytes(uint32_t nSlots)
 int b200sp_stage_reserve(b200sp_engine *e, uint32_t nSlots, void **slots)
 {
     if (!e || !slots || nSlots == 0) return fail(B200SP_EINVAL, "stage_reserve: bad argument");
-    CU_TRY(cudaSetDevice(e->device), "cudaSetDevice");
+    DeviceGuard guard;
+    CU_TRY(guard.enter(e->device), "cudaSetDevice");
     // the slot area starts at the offset the LARGEST reservation needs, so it never moves when fewer slots are used
     if (nSlots > e->stageSlots) {
         CU_TRY(cudaStreamSynchronize(e->stream), "sync before growing the staging area");
-        CU_TRY(grow_host(e->h_stage, e->h_stageCap, staged_sizes_bytes(nSlots) + static_cast<size_t>(nSlots) * B200SP_BLOCK_MAX),
+        CU_TRY(grow_host(e->h_slots, e->h_slotsCap, staged_sizes_bytes(nSlots) + static_cast<size_t>(nSlots) * B200SP_BLOCK_MAX),
                "cudaMallocHost(stage)");
         e->stageSlots = nSlots;
     }
-    *slots = e->h_stage + staged_sizes_bytes(e->stageSlots);
+    *slots = e->h_slots + staged_sizes_bytes(e->stageSlots);
     return B200SP_OK;
 }
 
@@ -568,7 +803,8 @@ int b200sp_parse_staged(b200sp_engine *e, const uint32_t *sizes, uint32_t nBlock
         if (sizes[b] == 0 || sizes[b] > B200SP_BLOCK_MAX) return fail(B200SP_EINVAL, "block size must be 1..131072");
         allFull = allFull && sizes[b] == B200SP_BLOCK_MAX;
     }
-    CU_TRY(cudaSetDevice(e->device), "cudaSetDevice");
+    DeviceGuard guard;
+    CU_TRY(guard.enter(e->device), "cudaSetDevice");
 
     const uint64_t stride = B200SP_BLOCK_MAX;
     const size_t seqStride = B200SP_SEQ_STRIDE, perBlockWorst = B200SP_BLOCK_MAX / 4 + 2;
@@ -587,8 +823,8 @@ int b200sp_parse_staged(b200sp_engine *e, const uint32_t *sizes, uint32_t nBlock
         e->h_goffsetsCap = nBlocks + 1 + nBlocks / 4;
     }
 
-    uint32_t *hSizes = reinterpret_cast<uint32_t *>(e->h_stage);
-    uint8_t *hBlocks = e->h_stage + sizesBytes;
+    uint32_t *hSizes = reinterpret_cast<uint32_t *>(e->h_slots);
+    uint8_t *hBlocks = e->h_slots + sizesBytes;
     uint8_t *dSizes = e->d_src, *dBlocks = e->d_src + sizesBytes;
     cudaStream_t st = e->stream;
     memcpy(hSizes, sizes, nBlocks * sizeof(uint32_t));
@@ -603,18 +839,42 @@ int b200sp_parse_staged(b200sp_engine *e, const uint32_t *sizes, uint32_t nBlock
                           reinterpret_cast<const uint32_t *>(dSizes), nBlocks, level,
                           reinterpret_cast<b200sp_sequence *>(e->d_seqs), seqStride, e->d_counts, st, e->d_work, 0);
     if (rc) return rc;
+    if (e->verify) {
+        CU_TRY(grow_dev(e->d_bad, e->d_badCap, nBlocks), "cudaMalloc(verify)");
+        if (!e->d_badTotal) CU_TRY(cudaMalloc(&e->d_badTotal, sizeof(uint32_t)), "cudaMalloc(verify total)");
+        if (!e->h_badTotal) CU_TRY(cudaMallocHost(&e->h_badTotal, sizeof(uint32_t)), "cudaMallocHost(verify total)");
+        CU_TRY(cudaMemsetAsync(e->d_badTotal, 0, sizeof(uint32_t), st), "memset(verify total)");
+        unsigned vgrid = (nBlocks + 3) / 4;
+        if (vgrid > static_cast<unsigned>(e->numSMs) * 16u) vgrid = e->numSMs * 16u;
+        verify_kernel<<<vgrid, 128, 0, st>>>(dBlocks, stride, static_cast<uint64_t>(nBlocks) * stride, B200SP_BLOCK_MAX,
+                                            reinterpret_cast<const uint32_t *>(dSizes), nBlocks, e->d_seqs, seqStride, e->d_counts, e->d_bad);
+        count_bad_kernel<<<8, 128, 0, st>>>(e->d_bad, nBlocks, e->d_badTotal);
+        CU_TRY(cudaGetLastError(), "launch verify_kernel");
+        CU_TRY(cudaMemcpyAsync(e->h_badTotal, e->d_badTotal, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H verify total");
+    }
     scan_counts_kernel<<<1, 32, 0, st>>>(e->d_counts, nBlocks, e->d_offsets);
     CU_TRY(cudaGetLastError(), "launch scan_counts_kernel");
     pack_kernel<<<e->numSMs * 2, kPostThreads, 0, st>>>(e->d_seqs, seqStride, e->d_counts, e->d_offsets, nBlocks, e->d_packed);
     CU_TRY(cudaGetLastError(), "launch pack_kernel");
     CU_TRY(cudaMemcpyAsync(e->h_counts, e->d_counts, nBlocks * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "D2H counts");
     CU_TRY(cudaMemcpyAsync(e->h_offsets, e->d_offsets, (nBlocks + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "D2H offsets");
-    CU_TRY(cudaStreamSynchronize(st), "sync after parse");
+    {
+        cudaError_t wce = cudaSuccess;
+        const int w = wait_stream(st, &wce);
+        if (w == 1) return fail(B200SP_ETIMEOUT, "no completion within 2 s");
+        if (w) return fail(B200SP_ECUDA, "sync after parse", wce);
+    }
+    if (e->verify && *e->h_badTotal != 0) return fail(B200SP_EVERIFY, "on-device verification rejected a block");
     const size_t total = static_cast<size_t>(e->h_offsets[nBlocks]);
     CU_TRY(grow_host(e->h_packed, e->h_packedCap, total + 1024), "cudaMallocHost(packed)");
     CU_TRY(cudaMemcpyAsync(e->h_packed, e->d_packed, total * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st), "D2H packed");
     for (uint32_t b = 0; b <= nBlocks; b++) e->h_goffsets[b] = e->h_offsets[b];
-    CU_TRY(cudaStreamSynchronize(st), "sync after D2H");
+    {
+        cudaError_t wce = cudaSuccess;
+        const int w = wait_stream(st, &wce);
+        if (w == 1) return fail(B200SP_ETIMEOUT, "no completion within 2 s");
+        if (w) return fail(B200SP_ECUDA, "sync after D2H", wce);
+    }
 
     res->nBlocks = nBlocks;
     res->counts = e->h_counts;
