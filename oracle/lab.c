@@ -15,7 +15,7 @@
 
 typedef struct {
     int cb, depth, coll, useLong, lb, full, cap, rep, repMin, repBonus, lazy, window, minMatch, hb, probe, tieNear;
-    int sb, sbytes, useShort, gainMode, backExt, evenOnly, skipBonus, repTie, repLong, seqRep, follow, followMin, harm, repK0; unsigned long long nFollow, nHarm;
+    int sb, sbytes, useShort, gainMode, backExt, evenOnly, skipBonus, repTie, repLong, seqRep, follow, followMin, harm, repK0, seqAbl; unsigned long long nFollow, nHarm;
     size_t nseq, nblocks, bad;
     unsigned long long steps, positions, litBytes, mlBytes, repHits, nMatch;
 } Lab;
@@ -186,7 +186,7 @@ static size_t lab_block(Lab *L, const uint8_t *src, size_t n, ZSTD_Sequence *out
         while (ip + 8 <= N) {
             uint32_t ml = 0, off = 0, start = ip; int isRep = 0;
             /* rep at ip+1 */
-            if (rep1 && ip + 1 >= rep1 && ip + 1 + 4 <= N && rd32(src + ip + 1) == rd32(src + ip + 1 - rep1)) {
+            if (!(L->seqAbl & 1) && rep1 && ip + 1 >= rep1 && ip + 1 + 4 <= N && rd32(src + ip + 1) == rd32(src + ip + 1 - rep1)) {
                 ml = common(src + ip + 1, src + ip + 1 - rep1, LIM(ip + 1)); off = rep1; start = ip + 1; isRep = 1;
             }
             if (ownLen[ip] > ml) { ml = ownLen[ip]; off = ownOff[ip]; start = ip; isRep = 0; }
@@ -197,7 +197,7 @@ static size_t lab_block(Lab *L, const uint8_t *src, size_t n, ZSTD_Sequence *out
                 for (int d = 1; d <= depth && !moved; d++) {
                     ip++;
                     if (ip + 8 > N) break;
-                    if (off && rep1 && ip >= rep1 && rd32(src + ip) == rd32(src + ip - rep1)) {
+                    if (!(L->seqAbl & 2) && off && rep1 && ip >= rep1 && rd32(src + ip) == rd32(src + ip - rep1)) {
                         const uint32_t mlRep = common(src + ip, src + ip - rep1, LIM(ip));
                         const int gain2 = (int)(mlRep * 3);
                         const int gain1 = (int)(ml * 3) - (int)(isRep ? 0 : floorlog2(off + 1)) + 1;
@@ -213,7 +213,7 @@ static size_t lab_block(Lab *L, const uint8_t *src, size_t n, ZSTD_Sequence *out
                 if (!moved) break;
             }
             /* catch up */
-            if (!isRep) while (start > anchorS && start > off && src[start - 1] == src[start - 1 - off]) { start--; ml++; }
+            if (!(L->seqAbl & 4) && !isRep) while (start > anchorS && start > off && src[start - 1] == src[start - 1 - off]) { start--; ml++; }
             if (!isRep) { rep2 = rep1; rep1 = off; }
             {
                 const uint32_t lit = start - anchorS;
@@ -222,7 +222,7 @@ static size_t lab_block(Lab *L, const uint8_t *src, size_t n, ZSTD_Sequence *out
             }
             ip = anchorS = start + ml;
             /* immediate rep2 */
-            while (ip + 4 <= N && rep2 && ip >= rep2 && rd32(src + ip) == rd32(src + ip - rep2)) {
+            while (!(L->seqAbl & 8) && ip + 4 <= N && rep2 && ip >= rep2 && rd32(src + ip) == rd32(src + ip - rep2)) {
                 const uint32_t m2 = common(src + ip, src + ip - rep2, LIM(ip));
                 if (m2 < 4) break;
                 { uint32_t t = rep2; rep2 = rep1; rep1 = t; }
@@ -353,12 +353,12 @@ int main(int argc, char **argv)
     L.full = env_int("LAB_FULL", 0); L.cap = env_int("LAB_CAP", 256); L.probe = env_int("LAB_PROBE", 16);
     L.rep = env_int("LAB_REP", 0); L.repMin = env_int("LAB_REPMIN", 4); L.repBonus = env_int("LAB_REPBONUS", 0);
     L.lazy = env_int("LAB_LAZY", 2); L.window = env_int("LAB_WINDOW", 32); L.minMatch = env_int("LAB_MINMATCH", 4);
-    L.gainMode = env_int("LAB_GAINMODE", 0); L.backExt = env_int("LAB_BACKEXT", 0); L.skipBonus = env_int("LAB_SKIPBONUS", 0); L.repTie = env_int("LAB_REPTIE", 0); L.repLong = env_int("LAB_REPLONG", 1); L.seqRep = env_int("LAB_SEQREP", 0); L.follow = env_int("LAB_FOLLOW", 0); g_hbytes = env_int("LAB_HBYTES", 4); L.harm = env_int("LAB_HARM", 0); L.repK0 = env_int("LAB_REPK0", 1); L.followMin = env_int("LAB_FOLLOWMIN", 8);
+    L.gainMode = env_int("LAB_GAINMODE", 0); L.backExt = env_int("LAB_BACKEXT", 0); L.skipBonus = env_int("LAB_SKIPBONUS", 0); L.repTie = env_int("LAB_REPTIE", 0); L.repLong = env_int("LAB_REPLONG", 1); L.seqRep = env_int("LAB_SEQREP", 0); L.follow = env_int("LAB_FOLLOW", 0); g_hbytes = env_int("LAB_HBYTES", 4); L.harm = env_int("LAB_HARM", 0); L.repK0 = env_int("LAB_REPK0", 1); L.seqAbl = env_int("LAB_SEQABL", 0); L.followMin = env_int("LAB_FOLLOWMIN", 8);
     g_useModel = env_int("LAB_MODEL", 0);
     seqmodel_params_for_level(level, &g_prm);
     g_prm.keyBytes = env_int("MODEL_KEYBYTES", g_prm.keyBytes); g_prm.rank16 = env_int("MODEL_RANK16", g_prm.rank16); g_prm.scan = env_int("MODEL_SCAN", g_prm.scan);
     g_prm.lazyDepth = env_int("MODEL_LAZY", g_prm.lazyDepth); g_prm.backExt = env_int("MODEL_BACKEXT", g_prm.backExt);
-    g_prm.minMatch = env_int("MODEL_MINMATCH", g_prm.minMatch); g_prm.extCap = env_int("MODEL_EXTCAP", g_prm.extCap);
+    g_prm.minMatch = env_int("MODEL_MINMATCH", g_prm.minMatch); g_prm.repParse = env_int("MODEL_REPPARSE", g_prm.repParse); g_prm.domBias = env_int("MODEL_DOMBIAS", g_prm.domBias); g_prm.extCap = env_int("MODEL_EXTCAP", g_prm.extCap);
     size_t calls, errs; int ok;
     size_t c = oracle_compress_with_producer(src, sz, chunk, level, lab_producer, &L, ZSTD_ps_enable, 0, 1, &calls, &errs, &ok);
     const char *base = strrchr(argv[1], '/'); base = base ? base + 1 : argv[1];

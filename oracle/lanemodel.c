@@ -80,6 +80,8 @@ size_t lanemodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t 
                        const SeqModelParams *prm)
 {
     if (n > (1u << 17) || outCap == 0 || prm->window != (int)KGRP) return (size_t)-1;
+    /* levels 5-12: the kernel's parse IS the serial one (one warp walks it, stage_rep_parse); nothing to restate */
+    if (prm->repParse) return seqmodel_block(src, n, out, outCap, prm);
     if (seqmodel_incompressible(src, n, prm)) {          /* step 0 of the model: one literal run */
         out[0].offset = 0; out[0].litLength = (uint32_t)n; out[0].matchLength = 0; out[0].rep = 0;
         return 1;

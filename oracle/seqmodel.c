@@ -45,17 +45,19 @@ void seqmodel_params_for_level(int level, SeqModelParams *prm)
 {
     /* One parameter class per zstd strategy class; the scan width is the level-scaled
      * search depth (the reference hands the level to its engine, /root/reference/src/qatseqprod.c:1154). */
-    static const int scanOf[13] = { 0, 4, 4, 4, 8, 32, 64, 96, 96, 128, 128, 256, 256 };
+    static const int scanOf[13] = { 0, 4, 4, 4, 8, 4, 8, 16, 24, 32, 64, 256, 320 };
     if (level < 1) level = 1;
     if (level > 12) level = 12;
-    prm->keyBytes = level == 1 ? 6 : level <= 4 ? 5 : 4;
+    prm->keyBytes = level <= 2 ? 6 : level <= 4 ? 5 : 4;
     prm->rank16 = level <= 4 ? 1 : 0;
     prm->scan = scanOf[level];
     prm->minMatch = 4;
     prm->extCap = 256;
-    prm->lazyDepth = level <= 4 ? 1 : 2;
-    prm->window = 32;            /* lazy look-ahead stays inside the 32-position group one warp owns */
-    prm->backExt = 1;
+    prm->lazyDepth = 2;
+    prm->window = 32;            /* fast classes: lazy look-ahead stays inside the 32-position group one warp owns */
+    prm->backExt = level <= 4 ? 1 : 0;   /* the repcode-aware parse catches up at take time instead */
+    prm->repParse = level <= 4 ? 0 : 1;
+    prm->domBias = level <= 4 ? 0 : -1;  /* fast classes probe the group's dominant offset; ties go to it */
 }
 
 typedef struct { uint32_t end, off; } BestMatch;   /* end = p + len (0 = none) */
@@ -114,14 +116,47 @@ int seqmodel_own_matches(const uint8_t *src, size_t n, const SeqModelParams *prm
                 if (prm->rank16 && ml < 4) ml = 0;
                 if (ml > bestLen) { bestLen = ml; bestOff = p - q; }      /* ties keep the nearer candidate */
             }
-            if (prm->rank16 && bestLen == MODEL_PROBE) {                  /* ... and extend only the winner */
-                const uint8_t *a = src + p, *c = src + p - bestOff;
-                while (bestLen < lim && a[bestLen] == c[bestLen]) bestLen++;
-            }
-            if (bestLen < (uint32_t)prm->minMatch) bestLen = 0;
         }
-        ownLen[p] = bestLen;
+        ownLen[p] = bestLen;            /* fast classes: still the rank on 16 bytes */
         ownOff[p] = bestLen ? bestOff : 0;
+        if (!prm->rank16) { if (ownLen[p] < (uint32_t)prm->minMatch) { ownLen[p] = 0; ownOff[p] = 0; } continue; }
+        if ((p & 31u) != 31u && p + 1 < N) continue;
+        /* ---- end of a 32-position group (fast classes): the dominant offset, then the long extension */
+        {
+            const uint32_t g0 = p & ~31u;
+            uint32_t D = 0;
+            if (prm->domBias >= 0) {
+                /* the offset most positions of the group chose (ties: the smaller one) ... */
+                uint32_t bestKey = 0;
+                for (uint32_t a = g0; a <= p; a++) {
+                    if (!ownLen[a]) continue;
+                    uint32_t cnt = 0;
+                    for (uint32_t c = g0; c <= p; c++) cnt += ownLen[c] && ownOff[c] == ownOff[a];
+                    const uint32_t key = (cnt << 17) | (0x1FFFFu - ownOff[a]);
+                    if (key > bestKey) bestKey = key;
+                }
+                if (bestKey) D = 0x1FFFFu - (bestKey & 0x1FFFFu);
+            }
+            for (uint32_t a = g0; a <= p; a++) {
+                uint32_t lim = a < nh ? N - a : 0;
+                if (lim > (uint32_t)prm->extCap) lim = (uint32_t)prm->extCap;
+                const uint32_t probe = lim > MODEL_PROBE ? MODEL_PROBE : lim;
+                /* ... is probed by every position of the group (the stand-in for zstd's repeated-offset probe: no
+                 * hash needed, so 4-byte matches between changed fields are found) and wins unless the scan's
+                 * winner is longer by more than domBias bytes */
+                if (D && a >= D && a < nh && ownOff[a] != D) {
+                    uint32_t ml = 0;
+                    while (ml < probe && src[a + ml] == src[a - D + ml]) ml++;
+                    if (ml >= 4 && ml + (uint32_t)prm->domBias >= ownLen[a]) { ownLen[a] = ml; ownOff[a] = D; }
+                }
+                if (ownLen[a] == MODEL_PROBE) {                            /* extend only the winner */
+                    uint32_t l = ownLen[a];
+                    while (l < lim && src[a + l] == src[a - ownOff[a] + l]) l++;
+                    ownLen[a] = l;
+                }
+                if (ownLen[a] < (uint32_t)prm->minMatch) { ownLen[a] = 0; ownOff[a] = 0; }
+            }
+        }
     }
     free(start); free(count); free(sorted);
     if (prm->backExt) {
@@ -173,6 +208,88 @@ int seqmodel_incompressible(const uint8_t *src, size_t n, const SeqModelParams *
     return hits < seqmodel_chance_threshold(nh);
 }
 
+/* Step 4 for levels 5-12: the serial, repcode-aware lazy parse (what one warp per block computes, see
+ * stage_rep_parse in lz77_kernels.cu).  It follows zstd's lazy parser in shape - repcode probe one byte ahead,
+ * look-ahead of lazyDepth positions with a cheaper price for the repeated offset, "catch up" to the left at
+ * take time, a second repeated offset tried right after every match - over the own matches of steps 1-2.
+ * rep1 / rep2 are the offsets of the last two emitted sequences with distinct offsets; repcode lengths are not
+ * capped (a capped own match is extended when it is taken). */
+static uint32_t common_len(const uint8_t *src, uint32_t a, uint32_t b, uint32_t lim)   /* b < a */
+{
+    uint32_t l = 0;
+    while (l < lim && src[a + l] == src[b + l]) l++;
+    return l;
+}
+
+static uint32_t rep_len(const uint8_t *src, uint32_t N, uint32_t p, uint32_t rep)
+{
+    if (!rep || p < rep || p + 4u > N) return 0;
+    if (rd32(src + p) != rd32(src + p - rep)) return 0;
+    return common_len(src, p, p - rep, N - p);
+}
+
+#define MODEL_CATCHUP 31u           /* bytes a taken match may grow to the left (one warp ballot) */
+
+static size_t rep_parse(const uint8_t *src, uint32_t N, const uint32_t *ownLen, const uint32_t *ownOff,
+                        ZSTD_Sequence *out, size_t outCap, const SeqModelParams *prm)
+{
+    const uint32_t nh = N >= 8 ? N - 7 : 0;
+    const uint32_t extCap = (uint32_t)prm->extCap;
+    size_t ns = 0;
+    uint32_t ip = 0, anchor = 0, rep1 = 0, rep2 = 0;
+    while (ip < nh) {
+        uint32_t r = rep_len(src, N, ip + 1, rep1);
+        uint32_t ml, off, start;
+        int isRep;
+        if (r == 0 && ownLen[ip] == 0) { ip++; continue; }
+        if (ownLen[ip] > r) { ml = ownLen[ip]; off = ownOff[ip]; start = ip; isRep = 0; }
+        else { ml = r; off = rep1; start = ip + 1; isRep = 1; }
+        for (;;) {                                      /* lazy look-ahead from ip */
+            int moved = 0;
+            for (uint32_t d = 1; d <= (uint32_t)prm->lazyDepth && !moved; d++) {
+                const uint32_t q = ip + d;
+                if (q >= nh) break;
+                const uint32_t rq = rep_len(src, N, q, rep1);
+                int32_t price = isRep ? 0 : (int32_t)floorlog2(off + 1u);
+                const uint32_t wgt = d == 1 ? 3u : 4u;                  /* zstd's weights for the repeated offset */
+                if (rq >= 4u && (int32_t)(rq * wgt) > (int32_t)(ml * wgt) - price + 1) {
+                    ml = rq; off = rep1; start = q; isRep = 1; price = 0;
+                }
+                if (ownLen[q] && gain_of(ownLen[q], ownOff[q]) > (int32_t)(ml * 4u) - price + (d == 1 ? 4 : 7)) {
+                    ml = ownLen[q]; off = ownOff[q]; start = q; isRep = 0;
+                    ip = q; moved = 1;
+                }
+            }
+            if (!moved) break;
+        }
+        if (!isRep) {
+            if (ml >= extCap) ml = common_len(src, start, start - off, N - start);      /* cut by the cap: extend */
+            uint32_t k = 0;                                                            /* catch up to the left */
+            while (k < MODEL_CATCHUP && start > anchor && start > off && src[start - 1] == src[start - 1 - off]) { start--; ml++; k++; }
+            if (off != rep1) { rep2 = rep1; rep1 = off; }
+        }
+        if (start == anchor && ns > 0 && out[ns - 1].offset == off) out[ns - 1].matchLength += ml;
+        else {
+            if (ns + 1 >= outCap) return (size_t)-1;
+            out[ns].offset = off; out[ns].litLength = start - anchor; out[ns].matchLength = ml; out[ns].rep = 0;
+            ns++;
+        }
+        ip = anchor = start + ml;
+        while (ip < nh) {                               /* the other repeated offset, right after the match */
+            const uint32_t m2 = rep_len(src, N, ip, rep2);
+            if (m2 < 4u) break;
+            { const uint32_t t = rep2; rep2 = rep1; rep1 = t; }
+            if (ns + 1 >= outCap) return (size_t)-1;
+            out[ns].offset = rep1; out[ns].litLength = 0; out[ns].matchLength = m2; out[ns].rep = 0;
+            ns++;
+            ip = anchor = ip + m2;
+        }
+    }
+    if (ns >= outCap) return (size_t)-1;
+    out[ns].offset = 0; out[ns].litLength = N - anchor; out[ns].matchLength = 0; out[ns].rep = 0;
+    return ns + 1;
+}
+
 size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t outCap,
                       const SeqModelParams *prm)
 {
@@ -189,6 +306,11 @@ size_t seqmodel_block(const uint8_t *src, size_t n, ZSTD_Sequence *out, size_t o
     if (!ownLen || !ownOff || !B || seqmodel_own_matches(src, n, prm, ownLen, ownOff) != 0) {
         free(ownLen); free(ownOff); free(B);
         return (size_t)-1;
+    }
+    if (prm->repParse) {
+        const size_t r = rep_parse(src, N, ownLen, ownOff, out, outCap, prm);
+        free(ownLen); free(ownOff); free(B);
+        return r;
     }
 
     /* step 3: run-max of match ends carried left to right */

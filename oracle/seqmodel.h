@@ -40,6 +40,9 @@ typedef struct {
     int lazyDepth;    /* 0 greedy, 1 lazy, 2 lazy2                                                         */
     int window;       /* lazy look-ahead never crosses a multiple of it (32 = one warp's group)            */
     int backExt;      /* 1: a position adopts the match of the next position (same 32-group) when it also holds one byte earlier */
+    int repParse;     /* 0: greedy/lazy parse over the propagated matches B (fast classes, lanemodel.c);
+                         1: serial repcode-aware lazy parse over the own matches (levels 5-12, one warp per block)  */
+    int domBias;      /* fast classes: >= 0 enables the dominant-offset probe; the scan's winner must be longer by more than this */
 } SeqModelParams;
 
 /* Parameters the kernels use for a zstd compression level (1..12). */

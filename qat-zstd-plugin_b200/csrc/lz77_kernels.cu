@@ -322,10 +322,15 @@ __device__ __forceinline__ uint4 ldg128_cg(const uint32_t *p)      // L2 only: t
 }
 
 // Tail shared by both extension variants: "catch up" by one byte, packed prefix maximum, group words.
+template <bool kOwnOnly>
 __device__ __forceinline__ void finish_group(const Shared &S, uint32_t idx, uint32_t slotC, uint32_t group, uint32_t lane,
                                              uint32_t p, uint32_t a0, uint32_t bestLen, uint32_t bestOff,
                                              uint32_t minMatch, uint32_t extCap)
 {
+    if (kOwnOnly) {         // levels 5-12: the serial repcode-aware parse reads every position's own match {len:9 | offset:17}
+        sts32(idx, bestLen ? (bestLen << 17) | bestOff : 0u);
+        return;
+    }
     const uint32_t in = S.in;
     // zstd's "catch up" by one byte: adopt the right neighbour's match if it also holds one byte earlier
     {
@@ -439,6 +444,25 @@ __device__ __forceinline__ void stage_extend_fast(const Shared &S, uint32_t w, u
         pick4(hi2, lo2, (s2 - 1u) & 3u, e);
     }
 
+    // The dominant offset of the group - the one most of its positions chose, the smaller one on ties - is probed by
+    // every position: the stand-in for zstd's repeated-offset probe.  It needs no hash, so the 4- and 5-byte matches
+    // between changed fields of record-like data are found, and a parse that keeps to one offset is what libzstd turns
+    // into repcodes.  It wins unless the scan's winner is longer on the 16 probe bytes.
+    {
+        const uint32_t m = __match_any_sync(0xFFFFFFFFu, bestLen ? bestOff : (0x20000u | lane));
+        const uint32_t key = bestLen ? (__popc(m) << 17) | (0x1FFFFu - bestOff) : 0u;
+        const uint32_t top = __reduce_max_sync(0xFFFFFFFFu, key);
+        const uint32_t D = top ? 0x1FFFFu - (top & 0x1FFFFu) : 0u;
+        const bool tryD = D != 0u && valid && p >= D && bestOff != D;
+        const uint32_t q = tryD ? p - D : 0u;
+        const uint32_t qa = in + (q & ~3u), sh = (q & 3u) * 8u;
+        const uint32_t y0 = ldsc32(qa), y1 = ldsc32(qa + 4u), y2 = ldsc32(qa + 8u), y3 = ldsc32(qa + 12u), y4 = ldsc32(qa + 16u);
+        const uint32_t b0 = __funnelshift_r(y0, y1, sh), b1 = __funnelshift_r(y1, y2, sh);
+        const uint32_t b2 = __funnelshift_r(y2, y3, sh), b3 = __funnelshift_r(y3, y4, sh);
+        const uint32_t ml = min(first_diff_16(a1 ^ b1, a2 ^ b2, a3 ^ b3), probe);
+        if (tryD && b0 == a0 && ml >= bestLen) { bestLen = ml; bestOff = D; }
+    }
+
     // Long extension of winners that filled the probe.  A lane continuing its predecessor's
     // match (same offset, both filled the probe) derives its length from the run head; heads are
     // extended by the whole warp, 128 bytes per step, far enough to serve all their followers.
@@ -472,7 +496,7 @@ __device__ __forceinline__ void stage_extend_fast(const Shared &S, uint32_t w, u
         if (myHead == h) bestLen = min(lim, U - (lane - h));
     }
     if (bestLen < minMatch) { bestLen = 0; bestOff = 0; }
-    finish_group(S, idx, slotC, group, lane, p, a0, bestLen, bestOff, minMatch, extCap);
+    finish_group<false>(S, idx, slotC, group, lane, p, a0, bestLen, bestOff, minMatch, extCap);
     if (kFuseHash) hash_finish(S, hashWindow, group, lane, hashNh, hs);
 }
 
@@ -553,7 +577,7 @@ __device__ __forceinline__ void stage_extend_full(const Shared &S, uint32_t w, u
         }
     }
     if (bestLen < minMatch) { bestLen = 0; bestOff = 0; }
-    finish_group(S, idx, slotC, group, lane, p, a0, bestLen, bestOff, minMatch, extCap);
+    finish_group<true>(S, idx, slotC, group, lane, p, a0, bestLen, bestOff, minMatch, extCap);
     if (kFuseHash) hash_finish(S, hashWindow, group, lane, hashNh, hs);
 }
 
@@ -815,6 +839,173 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------
+// R: the serial repcode-aware lazy parse of levels 5-12 (oracle/seqmodel.c:rep_parse is the normative text).
+// ONE warp per block walks the parse sequence by sequence; what is parallel is inside a step: 32 positions are
+// tested for "a match or a repeated-offset match starts here" at once, lengths at the repeated offsets are
+// measured 64 or 128 bytes per step, the catch-up to the left is one ballot.  All state is warp-uniform.
+// The bucket scans of these levels take several milliseconds per block; this walk hides behind them.
+// ------------------------------------------------------------------------------------------
+struct RepState {
+    uint32_t ip, anchor, rep1, rep2, nOut;
+    uint32_t openOff, openLit, openLen;     // the sequence being accumulated (openLen == 0: none)
+};
+
+// Common prefix of src[a..] and src[a - off..] from byte `from` on (the bytes before are known equal), whole warp,
+// 128 bytes per step, at most n - a.
+__device__ __forceinline__ uint32_t coop_len(uint32_t in, uint32_t a, uint32_t off, uint32_t from, uint32_t n, uint32_t lane)
+{
+    const uint32_t lim = n - a;
+    for (uint32_t k0 = from & ~3u; k0 < lim; k0 += 128u) {
+        const uint32_t k = k0 + lane * 4u;
+        uint32_t x = 1u;                                               // beyond the block: a difference at its first byte
+        if (k < lim) x = ld32u(in, a + k) ^ ld32u(in, a - off + k);
+        const uint32_t bad = __ballot_sync(0xFFFFFFFFu, x != 0u);
+        if (bad) {
+            const uint32_t l = __ffs(bad) - 1;
+            const uint32_t xl = __shfl_sync(0xFFFFFFFFu, x, l);
+            return min(lim, k0 + l * 4u + ((__ffs(xl) - 1) >> 3));
+        }
+    }
+    return lim;
+}
+
+__device__ __forceinline__ void rep_emit(RepState &st, uint4 *out, uint32_t lane, uint32_t off, uint32_t lit, uint32_t len)
+{
+    if (st.openLen && lane == 0) out[st.nOut] = make_uint4(st.openOff, st.openLit, st.openLen, 0u);
+    if (st.openLen) st.nOut++;
+    st.openOff = off; st.openLit = lit; st.openLen = len;
+}
+
+__device__ __forceinline__ void stage_rep_parse(const Shared &S, uint32_t w, uint32_t lane, uint32_t n, uint32_t nh,
+                                                uint32_t lazyDepth, uint32_t extCap, RepState &st, uint4 *out)
+{
+    const uint32_t in = S.in;
+    // own matches {len:9 | offset:17} are known below `avail` (this window's extension stage ended a stage ago); the
+    // last stage of a block knows them all (none exists from nh on).  The walk never reads further back than the
+    // window before this one.
+    const uint32_t wBase = w * kWindow;
+    const uint32_t avail = min(nh, wBase + kWindow);
+    const bool last = avail == nh;
+    const uint32_t rowCur = S.ringC + (w & (kRingC - 1)) * (kWindow * 4u), rowPrev = S.ringC + ((w - 1u) & (kRingC - 1)) * (kWindow * 4u);
+    uint32_t ip = st.ip, anchor = st.anchor, rep1 = st.rep1, rep2 = st.rep2;
+    uint32_t dec0 = 0;          // where the decision in progress started (it is taken up again from there when deferred)
+    bool chain = false;         // a decision is in progress and its best so far is the own match of `ip`
+    while (ip < avail) {
+        // ---- a span of 32 positions from ip: own match, its price-adjusted length, "the repeated offset matches here"
+        const uint32_t p = ip + lane;
+        uint32_t ow = 0;
+        if (p < avail) {
+            const uint32_t r = p >= wBase ? p - wBase : p + kWindow - wBase;
+            ow = lds32((p >= wBase ? rowCur : rowPrev) + ring_byte(r >> 5, r & 31u));
+        }
+        bool eq = false;
+        if (rep1 != 0u && p >= rep1 && p + 4u <= n) eq = ld32u(in, p) == ld32u(in, p - rep1);
+        const int32_t G = static_cast<int32_t>((ow >> 17) * 4u) - static_cast<int32_t>(31 - __clz((ow & 0x1FFFFu) + 1u));
+        const uint32_t ow1 = __shfl_down_sync(0xFFFFFFFFu, ow, 1), ow2 = __shfl_down_sync(0xFFFFFFFFu, ow, 2);
+        const int32_t G1 = __shfl_down_sync(0xFFFFFFFFu, G, 1), G2 = __shfl_down_sync(0xFFFFFFFFu, G, 2);
+        // the lazy step of a position whose best so far is its own match, repeated offset not involved (lanes 0..29)
+        const bool mv1 = lazyDepth >= 1u && ow1 != 0u && G1 > G + 4;
+        const bool mv2 = !mv1 && lazyDepth >= 2u && ow2 != 0u && G2 > G + 7;
+        const uint32_t H = __ballot_sync(0xFFFFFFFFu, ow != 0u), E = __ballot_sync(0xFFFFFFFFu, eq);
+        const uint32_t M1 = __ballot_sync(0xFFFFFFFFu, mv1), M2 = __ballot_sync(0xFFFFFFFFu, mv2);
+        const uint32_t C = H & ~(E >> 1) & ~(E >> 2);       // own match here, repeated offset silent one and two bytes on
+        const uint32_t lim = avail - ip;                    // positions of the span that are known (>= 1)
+        uint32_t s = 0;
+        if (!chain) {
+            // next position at which an own match starts or the repeated offset matches one byte further on
+            uint32_t starts = (H | (E >> 1)) & 0x7FFFFFFFu;      // lane 31 cannot see the byte after the span
+            if (lim < 32u) starts &= (1u << lim) - 1u;
+            if (!starts) { ip += min(lim, 31u); continue; }
+            s = __ffs(starts) - 1;
+            dec0 = ip + s;
+        }
+        uint32_t ml = 0, off = 0, start = 0;
+        bool isRep = false, done = false, defer = false;
+        while (!done) {
+            if (s > 29u) break;                                               // look-ahead leaves the span: move the span
+            if (!last && s + lazyDepth >= lim) { defer = true; break; }        // ... or needs the next window: next stage
+            const uint32_t base = ip + s;
+            if ((C >> s) & 1u) {
+                if ((M1 >> s) & 1u) { s += 1u; chain = true; continue; }
+                if ((M2 >> s) & 1u) { s += 2u; chain = true; continue; }
+                const uint32_t o0 = __shfl_sync(0xFFFFFFFFu, ow, s);
+                ml = o0 >> 17; off = o0 & 0x1FFFFu; start = base; isRep = false; done = true;
+                break;
+            }
+            // ---- the repeated offset is involved (oracle/seqmodel.c:rep_parse, one pass of its look-ahead loop):
+            // its lengths one and two bytes ahead, lanes 0-15 / 16-31, 64 bytes per half and step
+            uint32_t R1 = 0, R2 = 0;
+            {
+                const uint32_t h = lane >> 4, j = lane & 15u, q = base + 1u + h;
+                bool open = ((E >> (s + 1u + h)) & 1u) != 0u && (h == 0u || lazyDepth >= 2u);
+                uint32_t len = 0;
+                for (uint32_t k0 = 0; __any_sync(0xFFFFFFFFu, open); k0 += 64u) {
+                    const uint32_t k = k0 + j * 4u;
+                    uint32_t x = 1u;
+                    if (open && q + k < n) x = ld32u(in, q + k) ^ ld32u(in, q - rep1 + k);
+                    const uint32_t bad = (__ballot_sync(0xFFFFFFFFu, x != 0u) >> (h * 16u)) & 0xFFFFu;
+                    const uint32_t l = bad ? __ffs(bad) - 1 : 0u;
+                    const uint32_t xl = __shfl_sync(0xFFFFFFFFu, x, h * 16u + l);
+                    if (open && bad) { len = min(n - q, k0 + l * 4u + ((__ffs(xl) - 1) >> 3)); open = false; }
+                }
+                R1 = __shfl_sync(0xFFFFFFFFu, len, 0);
+                R2 = __shfl_sync(0xFFFFFFFFu, len, 16);
+            }
+            const uint32_t o0 = __shfl_sync(0xFFFFFFFFu, ow, s), o1 = __shfl_sync(0xFFFFFFFFu, ow, s + 1u), o2 = __shfl_sync(0xFFFFFFFFu, ow, s + 2u);
+            if (!chain && (o0 >> 17) <= R1) { ml = R1; off = rep1; start = base + 1u; isRep = true; }
+            else { ml = o0 >> 17; off = o0 & 0x1FFFFu; start = base; isRep = false; }
+            bool moved = false;
+#pragma unroll
+            for (uint32_t d = 1; d <= 2u; d++) {
+                if (d > lazyDepth || moved) break;
+                const uint32_t q = base + d;
+                if (q >= nh) break;
+                const uint32_t rq = d == 1u ? R1 : R2, oq = d == 1u ? o1 : o2, wgt = d == 1u ? 3u : 4u;
+                int32_t price = isRep ? 0 : static_cast<int32_t>(31 - __clz(off + 1u));
+                if (rq >= 4u && static_cast<int32_t>(rq * wgt) > static_cast<int32_t>(ml * wgt) - price + 1) {
+                    ml = rq; off = rep1; start = q; isRep = true; price = 0;
+                }
+                const uint32_t ol = oq >> 17, oo = oq & 0x1FFFFu;
+                if (ol && static_cast<int32_t>(ol * 4u) - static_cast<int32_t>(31 - __clz(oo + 1u)) >
+                              static_cast<int32_t>(ml * 4u) - price + (d == 1u ? 4 : 7)) {
+                    s += d; moved = true;
+                }
+            }
+            chain = true;
+            if (!moved) done = true;
+        }
+        if (defer) { ip = dec0; chain = false; break; }
+        if (!done) { ip += s; continue; }                                      // same decision, span moved to its base
+        chain = false;
+        if (!isRep) {
+            if (ml >= extCap) ml = coop_len(in, start, off, ml, n, lane);          // cut by the cap: extend
+            if (start > anchor) {
+                // catch up to the left: lane k tests byte start - k (k = 1..31)
+                const bool ok = lane >= 1u && start >= anchor + lane && start >= off + lane &&
+                                ((ldsc32(in + ((start - lane) & ~3u)) >> (((start - lane) & 3u) * 8u)) & 0xFFu) ==
+                                ((ldsc32(in + ((start - lane - off) & ~3u)) >> (((start - lane - off) & 3u) * 8u)) & 0xFFu);
+                const uint32_t k = __ffs(~(__ballot_sync(0xFFFFFFFFu, ok) >> 1)) - 1;    // leading run of lanes 1, 2, ...
+                start -= k; ml += k;
+            }
+            if (off != rep1) { rep2 = rep1; rep1 = off; }
+        }
+        if (start == anchor && st.openLen && st.openOff == off) st.openLen += ml;
+        else rep_emit(st, out, lane, off, start - anchor, ml);
+        ip = anchor = start + ml;
+        // ---- the other repeated offset, right after the match
+        while (ip < nh) {
+            if (rep2 == 0u || ip < rep2) break;
+            if (ld32u(in, ip) != ld32u(in, ip - rep2)) break;           // uniform
+            const uint32_t m2 = coop_len(in, ip, rep2, 4u, n, lane);
+            { const uint32_t t = rep2; rep2 = rep1; rep1 = t; }
+            rep_emit(st, out, lane, rep1, 0u, m2);
+            ip = anchor = ip + m2;
+        }
+    }
+    st.ip = ip; st.anchor = anchor; st.rep1 = rep1; st.rep2 = rep2;
+}
+
+// ------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------
 // Hits that chance alone produces in the repeated-key bitmap for nh insertions, plus six standard deviations:
@@ -967,6 +1158,7 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
 
         const uint32_t nW = (n + kWindow - 1) / kWindow;
         EmitCarry ec = {0, 0, 0};              // P2 (loaded from / published to shared memory every half window)
+        RepState rs = {0, 0, 0, 0, 0, 0, 0, 0};  // R (levels 5-12)
 
 #ifdef B200SP_ROLE_PROFILE
         unsigned long long busy = 0, blockStart = clock64();
@@ -1003,9 +1195,10 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
                 // spare warp
             } else if (role <= 4u) {
                 if (role == 3u && lane == 0) sts32(S.task + ((t + 1u) & 1u) * 4u, kEhWarps);   // next stage's queue (nobody touches it now)
-                if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, role - 3u, lane, P.minMatch, P.lazyDepth, P.errorFlag);
+                if (kFast) { if (t >= 3 && t - 3 < nW) stage_entries(S, t - 3, role - 3u, lane, P.minMatch, P.lazyDepth, P.errorFlag); }
+                else if (role == 3u && t >= 3 && t - 3 < nW) stage_rep_parse(S, t - 3, lane, n, nh, P.lazyDepth, P.extCap, rs, out);
             } else {
-                if (t >= 4) stage_emit(S, t - 4, role - 5u, lane, ec, out, P.errorFlag);
+                if (kFast && t >= 4) stage_emit(S, t - 4, role - 5u, lane, ec, out, P.errorFlag);
             }
 #ifdef B200SP_ROLE_PROFILE
             busy += clock64() - c0;
@@ -1019,9 +1212,14 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
             if (role == 6u) { atomicAdd(&P.roleCycles[7], clock64() - blockStart); atomicAdd(&P.roleCycles[8], (unsigned long long)(nW + 4)); }
         }
 #endif
-        if (role == 6u && lane == 0) {       // the second half's emit warp holds the carry after the last window
+        if (kFast && role == 6u && lane == 0) {       // the second half's emit warp holds the carry after the last window
             out[ec.nOut] = make_uint4(0u, n - ec.anchor, 0u, 0u);   // trailing literals / block delimiter
             P.counts[b] = ec.nOut + 1u;
+        }
+        if (!kFast && role == 3u && lane == 0) {
+            if (rs.openLen) out[rs.nOut++] = make_uint4(rs.openOff, rs.openLit, rs.openLen, 0u);
+            out[rs.nOut] = make_uint4(0u, n - rs.anchor, 0u, 0u);
+            P.counts[b] = rs.nOut + 1u;
         }
     }
 }
@@ -1034,14 +1232,14 @@ bool params_for_level(int level, ParseParams &p)
     // One parameter class per zstd strategy class; the scan width is the level-scaled search
     // depth (the reference hands the level to its engine, /root/reference/src/qatseqprod.c:1154, and rebuilds the
     // session when it changes, :1193-1201).  Must equal oracle/seqmodel.c:seqmodel_params_for_level.
-    static const uint32_t scanOf[13] = { 0, 4, 4, 4, 8, 32, 64, 96, 96, 128, 128, 256, 256 };
+    static const uint32_t scanOf[13] = { 0, 4, 4, 4, 8, 4, 8, 16, 24, 32, 64, 256, 320 };
     if (level < 1 || level > 12) return false;
-    p.keyMask = level == 1 ? 0xFFFFu : level <= 4 ? 0xFFu : 0u;   // 6-byte keys at level 1, 5-byte keys for the other fast/dfast levels, 4-byte keys from greedy up
-    p.rank16 = level <= 4 ? 1u : 0u;             // fast classes rank candidates on 16 bytes and extend the winner; the others measure every candidate in full
+    p.keyMask = level <= 2 ? 0xFFFFu : level <= 4 ? 0xFFu : 0u;   // 6-byte keys at levels 1-2, 5-byte keys at 3-4, 4-byte keys from greedy up
+    p.rank16 = level <= 4 ? 1u : 0u;             // fast classes rank candidates on 16 bytes and extend the winner; the others measure every candidate in full and parse repcode-aware
     p.scan = scanOf[level];
     p.minMatch = 4;
     p.extCap = kMaxExtCap;
-    p.lazyDepth = level <= 4 ? 1 : 2;
+    p.lazyDepth = 2;
     return true;
 }
 

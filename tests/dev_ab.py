@@ -33,7 +33,7 @@ def one():
     bad = 0; checked = 0
     sample = b"".join(data[o:o + BLOCK] for o in range(0, len(data), 97 * BLOCK)) + datagen.zeros(BLOCK) + \
         datagen.periodic(BLOCK, 100) + datagen.text_like(BLOCK + 777, 3)
-    for level in (1, 3, 6):
+    for level in (1, 3, 6, 12):
         f, seqs, counts, nb = parse(sample, level); f(); torch.cuda.synchronize()
         hc = counts.cpu().numpy(); hs = seqs.cpu().numpy().view(np.uint32)
         for b in range(nb):
@@ -45,23 +45,24 @@ def one():
                 if bad <= 4: print('   differs: level', level, 'block', b, 'counts', hc[b], len(want), flush=True)
     # timing
     out = []
-    for level in (3, 6):
-        f, seqs, counts, nb = parse(data, level)
+    for level in [int(x) for x in os.environ.get('DEV_AB_LEVELS', '3,6').split(',')]:
+        f, seqs, counts, nb = parse(data if level <= 4 else data[:148 * 4 * BLOCK], level)
         for _ in range(3): f()
         torch.cuda.synchronize()
         if os.environ.get("B200SP_ROLE_PROFILE"):
             buf = (ctypes.c_ulonglong * 10)(); pkg.lib.b200sp_debug_role_cycles(eng._h, buf)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(10): f()
+        reps = 10 if level <= 4 else 2
+        for _ in range(reps): f()
         e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
+        ms = e0.elapsed_time(e1) / reps
         role = ""
         if os.environ.get("B200SP_ROLE_PROFILE"):
             buf = (ctypes.c_ulonglong * 10)(); pkg.lib.b200sp_debug_role_cycles(eng._h, buf)
             r = list(buf); st = max(r[8], 1)
             role = f" [EH {r[0]/st/26:.0f} TL {r[1]/st:.0f} TS {r[2]/st:.0f} P1a {r[3]/st:.0f} P1b {r[4]/st:.0f} P2a {r[5]/st:.0f} P2b {r[6]/st:.0f} wall {r[7]/st:.0f}]"
-        out.append(f"L{level} {ms:.3f} ms {len(data)/ms/1e6:.1f} GB/s{role}")
+        out.append(f"L{level} {ms:.3f} ms {(len(data) if level <= 4 else 148 * 4 * BLOCK)/ms/1e6:.1f} GB/s{role}")
     print(f"{os.path.basename(pkg.LIB_PATH):24s} parity {checked - bad}/{checked}  " + "  ".join(out), flush=True)
 
 

@@ -35,7 +35,9 @@ def run(name, data, level=3, steps=5):
 data, label, info = corpus.load()
 run("image-corpus", data)
 if len(sys.argv) > 1 and sys.argv[1] == "all":
-    run("image-corpus L1", data, level=1); run("image-corpus L6", data, level=6)
+    run("image-corpus L1", data, level=1)
+    sub = data[:148 * 4 * BLOCK]
+    for lv in (5, 6, 7, 9, 12): run("corpus-head L%d" % lv, sub, level=lv, steps=2)
     M = 148 * 4 * BLOCK
     run("text_like", datagen.text_like(8 * BLOCK, 3) * (M // (8 * BLOCK)))
     run("records", datagen.records(M, 4))
