@@ -500,6 +500,38 @@ __device__ __forceinline__ void stage_extend_fast(const Shared &S, uint32_t w, u
     if (kFuseHash) hash_finish(S, hashWindow, group, lane, hashNh, hs);
 }
 
+// Levels 5-12 measure every candidate in full.  Common prefix of src[p..] and src[q..] (q < p), capped at lim, given
+// our first 16 bytes a0..a3; 0 when it cannot be longer than `beat` (the bytes around index `beat` are compared first:
+// most candidates of a deep scan fail there) or when the first four bytes differ.
+__device__ __forceinline__ uint32_t measure_full(uint32_t in, uint32_t p, uint32_t q, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                 uint32_t lim, uint32_t beat)
+{
+    if (beat >= 4u && ld32u(in, p + beat - 3u) != ld32u(in, q + beat - 3u)) return 0u;
+    const uint32_t qa = in + (q & ~3u), sh = (q & 3u) * 8u;
+    const uint32_t y0 = ldsc32(qa), y1 = ldsc32(qa + 4u), y2 = ldsc32(qa + 8u), y3 = ldsc32(qa + 12u), y4 = ldsc32(qa + 16u);
+    if (__funnelshift_r(y0, y1, sh) != a0) return 0u;
+    uint32_t ml = first_diff_16(a1 ^ __funnelshift_r(y1, y2, sh), a2 ^ __funnelshift_r(y2, y3, sh), a3 ^ __funnelshift_r(y3, y4, sh));
+    if (ml == kProbe) {
+        // 8 bytes per step: the alignments of both sides stay what they are (k advances by multiples of 4)
+        const uint32_t pa = in + (p & ~3u), psh = (p & 3u) * 8u;
+        uint32_t k = kProbe;
+        while (k < lim) {
+            const uint32_t x0 = ldsc32(pa + k), x1 = ldsc32(pa + k + 4u), x2 = ldsc32(pa + k + 8u);
+            const uint32_t z0 = ldsc32(qa + k), z1 = ldsc32(qa + k + 4u), z2 = ldsc32(qa + k + 8u);
+            const uint32_t d0 = __funnelshift_r(x0, x1, psh) ^ __funnelshift_r(z0, z1, sh), d1 = __funnelshift_r(x1, x2, psh) ^ __funnelshift_r(z1, z2, sh);
+            if (d0 | d1) { k += d0 ? low_byte_index(d0) : 4u + low_byte_index(d1); break; }
+            k += 8u;
+        }
+        ml = k;
+    }
+    return min(ml, lim);
+}
+
+#ifndef B200SP_COOP_MIN
+#define B200SP_COOP_MIN 32
+#endif
+constexpr uint32_t kCoopMin = B200SP_COOP_MIN;     // positions with more bucket entries to scan than this are scanned by the whole warp
+
 template <bool kFuseHash>
 __device__ __forceinline__ void stage_extend_full(const Shared &S, uint32_t w, uint32_t group, uint32_t lane,
                                              uint32_t p, uint32_t n, uint32_t nh, uint32_t minMatch,
@@ -524,8 +556,11 @@ __device__ __forceinline__ void stage_extend_full(const Shared &S, uint32_t w, u
     const uint32_t s = cw >> 14;
     const uint32_t avail = valid ? min(scan, cw & 0x3FFFu) : 0u;
     const uint32_t first = s - avail;
-    int32_t A = avail ? static_cast<int32_t>((s - 1u) >> 2) : -1;        // 16-byte chunk of the table we read next
-    const int32_t Alast = avail ? static_cast<int32_t>(first >> 2) : 0;
+    const bool shallow = avail != 0u && avail <= kCoopMin;
+    uint32_t deep = __ballot_sync(0xFFFFFFFFu, avail > kCoopMin);
+    // ---- short scans: every lane walks its own entries
+    int32_t A = shallow ? static_cast<int32_t>((s - 1u) >> 2) : -1;        // 16-byte chunk of the table we read next
+    const int32_t Alast = shallow ? static_cast<int32_t>(first >> 2) : 0;
     uint4 chunk = make_uint4(0u, 0u, 0u, 0u);
     if (A >= Alast) chunk = ldg128_cg(sorted + 4 * A);
     HashState hs = {0u, 0u};
@@ -551,29 +586,69 @@ __device__ __forceinline__ void stage_extend_full(const Shared &S, uint32_t w, u
                 pend ^= 1u << j;
                 const uint32_t e = j == 3u ? cur.w : j == 2u ? cur.z : j == 1u ? cur.y : cur.x;
                 const uint32_t q = e & 0x1FFFFu;
-                bool go = true;
-                if (bestLen >= kProbe) go = ld32u(in, p + bestLen - 3u) == ld32u(in, q + bestLen - 3u);   // cannot be longer otherwise
-                if (go) {
-                    const uint32_t qa = in + (q & ~3u), sh = (q & 3u) * 8u;
-                    const uint32_t y0 = ldsc32(qa), y1 = ldsc32(qa + 4u), y2 = ldsc32(qa + 8u), y3 = ldsc32(qa + 12u), y4 = ldsc32(qa + 16u);
-                    uint32_t ml = 0;
-                    if (__funnelshift_r(y0, y1, sh) == a0) {
-                        ml = first_diff_16(a1 ^ __funnelshift_r(y1, y2, sh), a2 ^ __funnelshift_r(y2, y3, sh), a3 ^ __funnelshift_r(y3, y4, sh));
-                        if (ml == kProbe) {
-                            uint32_t k = kProbe;
-                            while (k < lim) {
-                                const uint32_t x = ld32u(in, p + k) ^ ld32u(in, q + k);
-                                if (x) { k += (__ffs(x) - 1) >> 3; break; }
-                                k += 4u;
-                            }
-                            ml = k;
-                        }
-                        ml = min(ml, lim);
-                    }
-                    if (ml > bestLen) { bestLen = ml; bestOff = p - q; }
-                    if (bestLen >= lim) { pend = 0u; A = Alast - 1; }      // as long as a match can get: nothing farther can win
-                }
+                const uint32_t ml = measure_full(in, p, q, a0, a1, a2, a3, lim, bestLen);
+                if (ml > bestLen) { bestLen = ml; bestOff = p - q; }
+                if (bestLen >= lim) { pend = 0u; A = Alast - 1; }      // as long as a match can get: nothing farther can win
             }
+        }
+    }
+    // ---- deep scans: one position at a time, the whole warp on its bucket - 128 entries per step (one 16-byte chunk
+    // per lane, the nearest in lane 0), every lane measures the candidates among its four; the longest wins, the
+    // nearest on ties, and whatever a later step finds must be strictly longer (the serial order of the model)
+    // The chunk of the next step (of this position, else of the next deep position) is in flight while the current
+    // one is measured: a lone position would otherwise pay the table's L2 latency at every step.
+    {
+        uint32_t i = 32u, si = 0, firsti = 0;
+        int32_t A0 = 0, AlastI = 0;
+        uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+        auto next_position = [&]() {            // pops the next deep position and starts the load of its nearest entries
+            i = 32u;
+            if (deep) {
+                i = __ffs(deep) - 1;
+                deep &= deep - 1u;
+                si = __shfl_sync(0xFFFFFFFFu, s, i); firsti = __shfl_sync(0xFFFFFFFFu, first, i);
+                A0 = static_cast<int32_t>((si - 1u) >> 2); AlastI = static_cast<int32_t>(firsti >> 2);
+                const int32_t Al = A0 - static_cast<int32_t>(lane);
+                if (Al >= AlastI) nxt = ldg128_cg(sorted + 4 * Al);
+            }
+        };
+        next_position();
+        while (i < 32u) {
+            const uint32_t ci = i, cSi = si, cFirst = firsti;
+            const int32_t cAlast = AlastI;
+            const uint32_t limi = __shfl_sync(0xFFFFFFFFu, lim, ci), tagi = __shfl_sync(0xFFFFFFFFu, tag, ci);
+            const uint32_t c0 = __shfl_sync(0xFFFFFFFFu, a0, ci), c1 = __shfl_sync(0xFFFFFFFFu, a1, ci);
+            const uint32_t c2 = __shfl_sync(0xFFFFFFFFu, a2, ci), c3 = __shfl_sync(0xFFFFFFFFu, a3, ci);
+            const uint32_t pi = p - lane + ci;
+            uint32_t gLen = 0, gOff = 0;
+            for (;;) {
+                const uint4 c = nxt;
+                const int32_t Al = A0 - static_cast<int32_t>(lane);
+                const bool more = A0 - 32 >= cAlast;            // this position has a farther step
+                if (more) {
+                    A0 -= 32;
+                    const int32_t Aln = A0 - static_cast<int32_t>(lane);
+                    if (Aln >= cAlast) nxt = ldg128_cg(sorted + 4 * Aln);
+                } else next_position();
+                uint32_t lLen = gLen, lOff = 0;
+                if (Al >= cAlast) {
+                    const uint32_t i0 = 4u * static_cast<uint32_t>(Al);
+#pragma unroll
+                    for (int j = 3; j >= 0; j--) {
+                        const uint32_t e = j == 3 ? c.w : j == 2 ? c.z : j == 1 ? c.y : c.x;
+                        if ((e >> 17) == tagi && i0 + j >= cFirst && i0 + j < cSi) {
+                            const uint32_t q = e & 0x1FFFFu;
+                            const uint32_t ml = measure_full(in, pi, q, c0, c1, c2, c3, limi, lLen);
+                            if (ml > lLen) { lLen = ml; lOff = pi - q; }
+                        }
+                    }
+                }
+                const uint32_t top = __reduce_max_sync(0xFFFFFFFFu, lOff ? (lLen << 17) | (0x1FFFFu - lOff) : 0u);
+                if (top) { gLen = top >> 17; gOff = 0x1FFFFu - (top & 0x1FFFFu); }
+                if (!more) break;
+                if (gLen >= limi) { next_position(); break; }      // as long as a match can get: drop the farther steps
+            }
+            if (lane == ci) { bestLen = gLen; bestOff = gOff; }
         }
     }
     if (bestLen < minMatch) { bestLen = 0; bestOff = 0; }
@@ -1232,7 +1307,7 @@ bool params_for_level(int level, ParseParams &p)
     // One parameter class per zstd strategy class; the scan width is the level-scaled search
     // depth (the reference hands the level to its engine, /root/reference/src/qatseqprod.c:1154, and rebuilds the
     // session when it changes, :1193-1201).  Must equal oracle/seqmodel.c:seqmodel_params_for_level.
-    static const uint32_t scanOf[13] = { 0, 4, 4, 4, 8, 4, 8, 16, 24, 32, 64, 256, 320 };
+    static const uint32_t scanOf[13] = { 0, 4, 4, 4, 8, 4, 8, 16, 24, 32, 64, 256, 768 };
     if (level < 1 || level > 12) return false;
     p.keyMask = level <= 2 ? 0xFFFFu : level <= 4 ? 0xFFu : 0u;   // 6-byte keys at levels 1-2, 5-byte keys at 3-4, 4-byte keys from greedy up
     p.rank16 = level <= 4 ? 1u : 0u;             // fast classes rank candidates on 16 bytes and extend the winner; the others measure every candidate in full and parse repcode-aware
