@@ -74,12 +74,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 }
 
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier.
+// The input is read once: evict-first in L2, so that it does not push out the CTAs' sorted tables (the L2-resident
+// scratch every bucket scan reads).
 __device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        "{\n\t.reg .b64 pol;\n\t"
+        "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], pol;\n\t}"
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
         : "memory");
+}
+
+// ZSTD_Sequence stores: written once, read by a later kernel or the copy engine - streaming (evict-first) as well.
+__device__ __forceinline__ void st_seq(uint4 *p, uint32_t off, uint32_t lit, uint32_t len)
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(off), "r"(lit), "r"(len), "r"(0u) : "memory");
 }
 
 __device__ __forceinline__ void fence_proxy_async()
@@ -249,6 +259,8 @@ __device__ __forceinline__ void stage_table(const Shared &S, uint32_t w, uint32_
     const uint32_t rt = S.ringT + (w & 1u) * (kWindow * 2u);
     const uint32_t rc = S.ringC + (w & (kRingC - 1)) * (kWindow * 4u);
     const uint32_t windowBase = w * kWindow;
+    uint64_t polLast;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(polLast));
 #pragma unroll 1
     for (uint32_t g0 = 0; g0 < kGroups; g0 += kTUnroll) {
         uint32_t hw[kTUnroll], tg[kTUnroll], old[kTUnroll];
@@ -278,7 +290,8 @@ __device__ __forceinline__ void stage_table(const Shared &S, uint32_t w, uint32_
             const uint32_t e = __shfl_sync(0xFFFFFFFFu, old[k], (hw[k] >> 18) & 31u);
             const uint32_t idx = (e & 0x1FFFFu) + ((hw[k] >> 13) & 31u);
             const uint32_t slot = (e >> 17) * kSegAlign + idx;
-            if (valid) sorted[slot] = (windowBase + (g0 + k) * 32u + lane) | (tg[k] << 17);
+            // evict-last: the table is this CTA's working set in L2 for the whole block
+            if (valid) asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(sorted + slot), "r"((windowBase + (g0 + k) * 32u + lane) | (tg[k] << 17)), "l"(polLast) : "memory");
             sts32(rc + ring_byte(g0 + k, lane), valid ? (slot << 14) | min(idx, kIdxCap) : 0u);
         }
     }
@@ -528,7 +541,7 @@ __device__ __forceinline__ uint32_t measure_full(uint32_t in, uint32_t p, uint32
 }
 
 #ifndef B200SP_COOP_MIN
-#define B200SP_COOP_MIN 32
+#define B200SP_COOP_MIN 128
 #endif
 constexpr uint32_t kCoopMin = B200SP_COOP_MIN;     // positions with more bucket entries to scan than this are scanned by the whole warp
 
@@ -890,13 +903,13 @@ __device__ __forceinline__ void stage_emit(const Shared &S, uint32_t w, uint32_t
             if (lit == 0 && o == prevOff && anchor > 0) {
                 if (haveOpen) openLen += len; else headAdd += len;
             } else {
-                if (haveOpen) out[outIdx++] = make_uint4(openOff, openLit, openLen, 0u);
+                if (haveOpen) st_seq(out + outIdx++, openOff, openLit, openLen);
                 openOff = o; openLit = lit; openLen = len; haveOpen = true;
             }
             anchor = end; prevOff = o;
             cur = L >> 22;
         }
-        if (haveOpen) out[outIdx] = make_uint4(openOff, openLit, openLen, 0u);
+        if (haveOpen) st_seq(out + outIdx, openOff, openLit, openLen);
     }
     __syncwarp();
     // A continuation is added to a sequence an earlier lane wrote - for the second half possibly a lane of the
@@ -946,7 +959,7 @@ __device__ __forceinline__ uint32_t coop_len(uint32_t in, uint32_t a, uint32_t o
 
 __device__ __forceinline__ void rep_emit(RepState &st, uint4 *out, uint32_t lane, uint32_t off, uint32_t lit, uint32_t len)
 {
-    if (st.openLen && lane == 0) out[st.nOut] = make_uint4(st.openOff, st.openLit, st.openLen, 0u);
+    if (st.openLen && lane == 0) st_seq(out + st.nOut, st.openOff, st.openLit, st.openLen);
     if (st.openLen) st.nOut++;
     st.openOff = off; st.openLit = lit; st.openLen = len;
 }
@@ -1307,7 +1320,7 @@ bool params_for_level(int level, ParseParams &p)
     // One parameter class per zstd strategy class; the scan width is the level-scaled search
     // depth (the reference hands the level to its engine, /root/reference/src/qatseqprod.c:1154, and rebuilds the
     // session when it changes, :1193-1201).  Must equal oracle/seqmodel.c:seqmodel_params_for_level.
-    static const uint32_t scanOf[13] = { 0, 4, 4, 4, 8, 4, 8, 16, 24, 32, 64, 256, 768 };
+    static const uint32_t scanOf[13] = { 0, 4, 4, 4, 8, 16, 24, 32, 32, 48, 64, 256, 768 };
     if (level < 1 || level > 12) return false;
     p.keyMask = level <= 2 ? 0xFFFFu : level <= 4 ? 0xFFu : 0u;   // 6-byte keys at levels 1-2, 5-byte keys at 3-4, 4-byte keys from greedy up
     p.rank16 = level <= 4 ? 1u : 0u;             // fast classes rank candidates on 16 bytes and extend the winner; the others measure every candidate in full and parse repcode-aware
