@@ -53,6 +53,42 @@ def test_ragged_sizes(pkg, oracle, engine, n):
     assert got[-1, 0] == 0 and got[-1, 2] == 0          # last entry = trailing literals (reference convention)
 
 
+@pytest.mark.parametrize("level", [5, 6, 9, 12])
+def test_rep_parse_ragged_sizes_and_window_edges(pkg, oracle, engine, level):
+    """Levels 5-12 (the serial repcode-aware parse on one warp): sizes around 0, the 8-byte hash limit, the 32-position
+    span and the 1664-position pipeline window (a decision whose look-ahead needs the next window is deferred), in ONE
+    batch with per-block sizes; repetitive and record-like content so that repeated offsets, capped matches (> 256 B)
+    and rep2 matches occur right at the edges."""
+    W = 1664
+    sizes = [0, 1, 7, 8, 9, 12, 31, 32, 33, 40, W - 3, W - 2, W - 1, W, W + 1, W + 2, W + 9, 2 * W - 1, 2 * W, 2 * W + 1,
+             3 * W + 5, 5000, 65535, 65536, 70001, 131071, 131072]
+    stride = 131072
+    buf = bytearray(stride * len(sizes))
+    for i, n in enumerate(sizes):
+        kind = i % 4
+        blk = (datagen.records(n + 1, seed=300 + i) if kind == 0 else datagen.text_like(n + 1, seed=300 + i) if kind == 1
+               else datagen.periodic(n + 1, 37 + i, seed=i) if kind == 2 else (datagen.text_like(700, seed=i) * (n // 700 + 1)))
+        buf[i * stride:i * stride + n] = blk[:n]
+    counts, seqs, bad = parse_on_gpu(pkg, engine, bytes(buf), level=level, sizes=sizes, stride=stride)
+    for i, n in enumerate(sizes):
+        blk = bytes(buf[i * stride:i * stride + n])
+        got = seqs[i, :counts[i]]
+        want = oracle.model_block(blk, level)
+        assert bad[i] == 0, f"size {n}: verifier {bad[i]}"
+        assert oracle.validate(blk, got) == 0, f"size {n}: does not replay"
+        assert got.shape == want.shape and (got == want).all(), f"size {n} (level {level})"
+
+
+def test_rep_parse_special_content(pkg, oracle, engine):
+    """Zeros (one 128 KiB match through the uncapped extension), short periods, and two alternating offsets."""
+    a, b = datagen.rand_bytes(48, 7), datagen.rand_bytes(80, 8)
+    alt = (a + b[:5] + a + b) * 1100
+    data = datagen.zeros(BLOCK) + datagen.periodic(BLOCK, 3) + datagen.periodic(BLOCK, 255) + alt[:BLOCK] + \
+        datagen.rand_bytes(BLOCK // 2, 9) + datagen.zeros(BLOCK // 2)
+    for level in (6, 12):
+        check_against_model(pkg, oracle, engine, data, level=level)
+
+
 def test_small_block_sizes_and_strides(pkg, oracle, engine):
     """blockSize < 128 KiB (the reference benchmark's -c 32K/64K chunks) and explicit per-block sizes."""
     data = datagen.mixed_corpus(700000, seed=31)
