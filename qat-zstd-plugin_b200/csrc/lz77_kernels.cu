@@ -1138,8 +1138,17 @@ __global__ void __launch_bounds__(kThreads, 1) lz77_parse_kernel(const ParsePara
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // Role of this warp: 0 = hash/extend pool, 1 = bucket counters (T), 2 = spare, 3 / 4 = entries of the first /
     // second half window (P1), 5 / 6 = emit of the first / second half window (P2).
-    const uint32_t role = warp < kEhWarps ? 0u : warp - kEhWarps + 1u;
-    const uint32_t poolIdx = warp;
+    // Which warp plays which role.  Levels 5-12: the table warp and the parse warp sit on one scheduler (warps 3, 7 of
+    // sub-partition 3; the idle entry/emit warps take 11, 15, 19) and share it with three pool warps instead of
+    // six or seven: the parse warp is the longest role there and an issue slot lost to a pool warp is lost time
+    // (parse warp 118 K -> 105 K cycles per stage).  Levels 1-4 gain nothing from it (the pool becomes the longest role).
+    uint32_t vw = warp;
+    if (!kFast)
+        vw = warp == 3u ? 26u : warp == 26u ? 3u :
+             warp == 7u ? 28u : warp == 11u ? 29u : warp == 15u ? 30u : warp == 19u ? 31u :
+             warp == 28u ? 7u : warp == 29u ? 11u : warp == 30u ? 15u : warp == 31u ? 19u : warp;
+    const uint32_t role = vw < kEhWarps ? 0u : vw - kEhWarps + 1u;
+    const uint32_t poolIdx = vw;
     uint32_t *sorted = P.sorted + static_cast<size_t>(blockIdx.x) * kSortedCap;
 
     if (tid == 0) {
