@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -62,33 +63,43 @@ double now_seconds()
 }
 
 // 0 = done, 1 = timed out, otherwise the CUDA error
+// Polling discipline shared by both waits: a few dozen back-to-back queries catch short waits quickly, then the
+// thread sleeps between queries with a growing interval (20 us ... 200 us).  Every query takes a driver lock: with
+// one or two engines per compressing thread, thousands of spinning queries slow down everybody's launches.
+struct Backoff {
+    double deadline = now_seconds() + kTimeoutSeconds;
+    unsigned polls = 0;
+    long sleepNs = 20000;
+    bool expired()          // call after an unsuccessful query; true = give up
+    {
+        if (++polls <= 64) return false;
+        if (now_seconds() > deadline) return true;
+        timespec ts = {0, sleepNs};
+        nanosleep(&ts, nullptr);
+        if (sleepNs < 200000) sleepNs += sleepNs / 2;
+        return false;
+    }
+};
+
 int wait_event(cudaEvent_t ev, cudaError_t *ce)
 {
-    const double deadline = now_seconds() + kTimeoutSeconds;
-    for (unsigned spins = 0;; spins++) {
+    Backoff b;
+    for (;;) {
         const cudaError_t q = cudaEventQuery(ev);
         if (q == cudaSuccess) return 0;
         if (q != cudaErrorNotReady) { *ce = q; return 2; }
-        if (spins > 2000) {         // the first ~2000 polls spin (short waits stay short), then yield
-            if (now_seconds() > deadline) return 1;
-            timespec ts = {0, 20000};
-            nanosleep(&ts, nullptr);
-        }
+        if (b.expired()) return 1;
     }
 }
 
 int wait_stream(cudaStream_t st, cudaError_t *ce)
 {
-    const double deadline = now_seconds() + kTimeoutSeconds;
-    for (unsigned spins = 0;; spins++) {
+    Backoff b;
+    for (;;) {
         const cudaError_t q = cudaStreamQuery(st);
         if (q == cudaSuccess) return 0;
         if (q != cudaErrorNotReady) { *ce = q; return 2; }
-        if (spins > 2000) {
-            if (now_seconds() > deadline) return 1;
-            timespec ts = {0, 20000};
-            nanosleep(&ts, nullptr);
-        }
+        if (b.expired()) return 1;
     }
 }
 
@@ -112,13 +123,33 @@ void parallel_copy(void *dst, const void *src, size_t bytes)
     for (auto &t : th) t.join();
 }
 
+// What an engine needs to know about a device, asked once per process: cudaGetDeviceProperties takes milliseconds
+// and a driver-wide lock, and engines are created by the dozen (one or two per compressing thread).
+struct DeviceFacts { int state; int numSMs; };        // state: 0 unknown, 1 usable, -1 not usable
+static DeviceFacts g_facts[64];
+static std::mutex g_factsMu;
+
+static DeviceFacts device_facts(int dev)
+{
+    if (dev < 0 || dev >= 64) return DeviceFacts{-1, 0};
+    std::lock_guard<std::mutex> lock(g_factsMu);
+    if (g_facts[dev].state == 0) {
+        int major = 0, minor = 0, optin = 0, sms = 0;
+        const bool ok = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
+                        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) == cudaSuccess &&
+                        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
+                        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess;
+        if (!ok) { (void)cudaGetLastError(); return DeviceFacts{-1, 0}; }       // not cached: the driver may come up later
+        // the cubin is sm_100a only; the parser needs the 227 KB opt-in shared memory carve-out
+        g_facts[dev].state = (major == 10 && minor == 0 && static_cast<size_t>(optin) >= static_cast<size_t>(b200sp::kSmemTotal)) ? 1 : -1;
+        g_facts[dev].numSMs = sms;
+    }
+    return g_facts[dev];
+}
+
 bool device_usable(int dev)
 {
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return false;
-    // the cubin is sm_100a only; the parser needs the 227 KB opt-in shared memory carve-out
-    return prop.major == 10 && prop.minor == 0 &&
-           prop.sharedMemPerBlockOptin >= static_cast<size_t>(b200sp::kSmemTotal);
+    return device_facts(dev).state == 1;
 }
 
 // ---- wire format: offset | litLength << 17 | matchLength << 35 ----------------------------
@@ -357,14 +388,19 @@ int b200sp_engine_create(int device, b200sp_engine **out)
     if (!device_usable(device)) return fail(B200SP_EUNSUPPORTED, "device is not sm_100 with 227 KB shared memory per CTA");
     DeviceGuard guard;
     CU_TRY(guard.enter(device), "cudaSetDevice");
-    CU_TRY(b200sp::configure_kernels(), "cudaFuncSetAttribute(max dynamic smem)");
+    {
+        static bool configured[64];
+        std::lock_guard<std::mutex> lock(g_factsMu);
+        if (!configured[device]) {
+            CU_TRY(b200sp::configure_kernels(), "cudaFuncSetAttribute(max dynamic smem)");
+            configured[device] = true;
+        }
+    }
     b200sp_engine *e = static_cast<b200sp_engine *>(calloc(1, sizeof(b200sp_engine)));
     if (!e) return fail(B200SP_ENOMEM, "engine_create: out of host memory");
     e->device = device;
     { const char *v = getenv("QZSTD_VERIFY"); e->verify = (v && *v && *v != '0') ? 1 : 0; }
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, device);
-    e->numSMs = prop.multiProcessorCount;
+    e->numSMs = device_facts(device).numSMs;
     ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->sIn, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->sOut, cudaStreamNonBlocking);
@@ -381,7 +417,8 @@ int b200sp_engine_create(int device, b200sp_engine **out)
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e->evDone[k], cudaEventDisableTiming);
     }
     if (ce == cudaSuccess) ce = cudaMalloc(&e->d_work, 256);
-    if (ce == cudaSuccess) ce = cudaMemset(e->d_work, 0, 256);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(e->d_work, 0, 256, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
     if (ce == cudaSuccess) ce = cudaMalloc(&e->d_chunkWork, kMaxChunks * sizeof(unsigned int));
     if (ce == cudaSuccess) ce = cudaMallocHost(&e->h_flag, sizeof(uint32_t));
     if (ce == cudaSuccess) *e->h_flag = 0;
@@ -775,6 +812,36 @@ static size_t staged_sizes_bytes(uint32_t nSlots)
     return (static_cast<size_t>(nSlots) * sizeof(uint32_t) + 15u) & ~static_cast<size_t>(15);
 }
 
+// Buffers of the staged path, sized for the whole reservation at once: growing in steps means cudaFree, which waits
+// for every stream of the device - with many engines at work (one or two per compressing thread) each step stalls
+// all of them.  The parser's table scratch is included for the same reason.
+static int reserve_staged_buffers(b200sp_engine *e)
+{
+    const uint64_t stride = B200SP_BLOCK_MAX;
+    const size_t seqStride = B200SP_SEQ_STRIDE, perBlockWorst = B200SP_BLOCK_MAX / 4 + 2;
+    const size_t sizesBytes = staged_sizes_bytes(e->stageSlots);
+    const size_t capBlocks = e->stageSlots;
+    CU_TRY(grow_dev(e->d_src, e->d_srcCap, sizesBytes + capBlocks * stride + 16), "cudaMalloc(src)");
+    CU_TRY(grow_dev(e->d_seqs, e->d_seqsCap, capBlocks * seqStride), "cudaMalloc(seqs)");
+    CU_TRY(grow_dev(e->d_counts, e->d_countsCap, capBlocks), "cudaMalloc(counts)");
+    CU_TRY(grow_dev(e->d_offsets, e->d_offsetsCap, capBlocks + kMaxChunks), "cudaMalloc(offsets)");
+    CU_TRY(grow_dev(e->d_packed, e->d_packedCap, capBlocks * perBlockWorst), "cudaMalloc(packed)");
+    CU_TRY(grow_host(e->h_counts, e->h_countsCap, capBlocks), "cudaMallocHost(counts)");
+    CU_TRY(grow_host(e->h_offsets, e->h_offsetsCap, capBlocks + kMaxChunks), "cudaMallocHost(offsets)");
+    CU_TRY(grow_host(e->h_packed, e->h_packedCap, capBlocks * (B200SP_BLOCK_MAX / 12) + 1024), "cudaMallocHost(packed)");
+    {
+        const size_t grid = capBlocks < static_cast<size_t>(e->numSMs) ? capBlocks : static_cast<size_t>(e->numSMs);
+        const size_t want = grid * b200sp::kSortedCap;
+        if (want > e->d_sortedCap[0]) {
+            cudaFree(e->d_sorted[0]);
+            e->d_sorted[0] = nullptr; e->d_sortedCap[0] = 0;
+            CU_TRY(cudaMalloc(&e->d_sorted[0], want * sizeof(uint32_t)), "cudaMalloc(sorted-table scratch)");
+            e->d_sortedCap[0] = want;
+        }
+    }
+    return B200SP_OK;
+}
+
 int b200sp_stage_reserve(b200sp_engine *e, uint32_t nSlots, void **slots)
 {
     if (!e || !slots || nSlots == 0) return fail(B200SP_EINVAL, "stage_reserve: bad argument");
@@ -788,7 +855,7 @@ int b200sp_stage_reserve(b200sp_engine *e, uint32_t nSlots, void **slots)
         e->stageSlots = nSlots;
     }
     *slots = e->h_slots + staged_sizes_bytes(e->stageSlots);
-    return B200SP_OK;
+    return reserve_staged_buffers(e);       // everything the staged parse of that many blocks needs, now rather than inside it
 }
 
 int b200sp_parse_staged(b200sp_engine *e, const uint32_t *sizes, uint32_t nBlocks, int level, b200sp_result *res)
@@ -807,15 +874,9 @@ int b200sp_parse_staged(b200sp_engine *e, const uint32_t *sizes, uint32_t nBlock
     CU_TRY(guard.enter(e->device), "cudaSetDevice");
 
     const uint64_t stride = B200SP_BLOCK_MAX;
-    const size_t seqStride = B200SP_SEQ_STRIDE, perBlockWorst = B200SP_BLOCK_MAX / 4 + 2;
+    const size_t seqStride = B200SP_SEQ_STRIDE;
     const size_t sizesBytes = staged_sizes_bytes(e->stageSlots);
-    CU_TRY(grow_dev(e->d_src, e->d_srcCap, sizesBytes + static_cast<size_t>(e->stageSlots) * stride + 16), "cudaMalloc(src)");
-    CU_TRY(grow_dev(e->d_seqs, e->d_seqsCap, nBlocks * seqStride), "cudaMalloc(seqs)");
-    CU_TRY(grow_dev(e->d_counts, e->d_countsCap, nBlocks), "cudaMalloc(counts)");
-    CU_TRY(grow_dev(e->d_offsets, e->d_offsetsCap, nBlocks + kMaxChunks), "cudaMalloc(offsets)");
-    CU_TRY(grow_dev(e->d_packed, e->d_packedCap, nBlocks * perBlockWorst), "cudaMalloc(packed)");
-    CU_TRY(grow_host(e->h_counts, e->h_countsCap, nBlocks), "cudaMallocHost(counts)");
-    CU_TRY(grow_host(e->h_offsets, e->h_offsetsCap, nBlocks + kMaxChunks), "cudaMallocHost(offsets)");
+    { const int rcAlloc = reserve_staged_buffers(e); if (rcAlloc) return rcAlloc; }
     if (e->h_goffsetsCap < nBlocks + 1) {
         free(e->h_goffsets);
         e->h_goffsets = static_cast<unsigned long long *>(malloc((nBlocks + 1 + nBlocks / 4) * sizeof(unsigned long long)));

@@ -17,13 +17,20 @@
  *                                                    exhaustion answers ERROR, never blocks
  *   QZSTD_decLz4s (:1013-1091)                       b200sp_expand: 8-byte wire format -> ZSTD_Sequence
  */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE             /* process_vm_readv */
+#endif
 #include "qatseqprod.h"
 #include "b200seqprod.h"
 
+#include <errno.h>
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/uio.h>
+#include <time.h>
+#include <unistd.h>
 
 #define KB                            (1024)
 #define COMP_LVL_MINIMUM              (1)
@@ -31,6 +38,7 @@
 #define NUM_BLOCK_OF_RETRY_INTERVAL   (1000)     /* /root/reference/src/qatseqprod.c:88 */
 
 #define QZSTD_MAX_DEVICES 16
+#define QZSTD_RA_MAX      64         /* blocks read ahead at most (8 MiB) */
 
 typedef struct {
     int status;                 /* QZSTD_FAIL / QZSTD_STARTED / QZSTD_OK */
@@ -47,6 +55,16 @@ static void coalesce_start_if_wanted(void);     /* cross-thread coalescing, furt
 static void coalesce_stop(void);
 static void coalesce_enable_from_env(void);
 
+typedef struct {                    /* a window of the caller's memory read ahead and parsed as one batch */
+    const unsigned char *base;      /* application address of block 0, NULL = none */
+    unsigned char *slots;           /* the engine's pinned copy, one block per 128 KiB slot */
+    size_t block;                   /* nominal block size */
+    uint32_t blocks, want;          /* blocks parsed / asked for */
+    uint32_t sizes[QZSTD_RA_MAX];
+    int level;
+    b200sp_result batch;
+} QZSTD_Window;
+
 typedef struct {
     b200sp_engine *engine;          /* lazily created on the first offloaded block */
     int device;                     /* the device this state was dealt, -1 before the first block */
@@ -57,6 +75,27 @@ typedef struct {
     int batchLevel;                 /* level the cached batch was parsed at, 0 = no batch */
     size_t served;                  /* blocks of the cached batch handed out so far */
     b200sp_result batch;
+    /* transparent read-ahead (no hint): see read_ahead() */
+    const unsigned char *lastSrc;   /* the previous callback's block ... */
+    size_t lastSize;                /* ... and its size */
+    unsigned int streak;            /* consecutive callbacks that started where the previous one ended, same size */
+    QZSTD_Window win[2];            /* win[cur] is being served, win[cur ^ 1] is what the helper thread fills next */
+    int cur;
+    b200sp_engine *engine2;         /* engine of win[1] (win[0] uses `engine`), created with the helper thread */
+    /* helper thread: fills the next window while libzstd entropy-codes the blocks of the current one */
+    pthread_t raThread;
+    int raThreadUp;                 /* 1: thread running, -1: could not be started (no prefetch, windows still work) */
+    pthread_mutex_t raMu;
+    pthread_cond_t raCv;
+    int raBusy;                     /* a request is posted or being worked on */
+    volatile int raReady;           /* the helper's engine exists: requests may be posted */
+    int raFailed;                   /* ... or could not be created: no prefetching for this state */
+    int raQuit;
+    const unsigned char *raReqSrc;  /* the request: fill win[raReqWin] from raReqSrc */
+    size_t raReqSize;
+    int raReqLevel, raReqWin;
+    uint32_t raReqWant;
+    unsigned long long prefetched;  /* windows the helper had ready when they were asked for */
     /* counters */
     unsigned long long calls, errors, batched;
 } QZSTD_State_T;
@@ -79,6 +118,13 @@ static int force_error(void)
      * (ZSTD_c_enableSeqProducerFallback) can be exercised on a healthy device */
     const char *e = getenv("QZSTD_FORCE_ERROR");
     return e && *e && *e != '0';
+}
+
+static double ra_now(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
 }
 
 const char *QZSTD_version(void)
@@ -147,17 +193,39 @@ void QZSTD_stopQatDevice(void)
     pthread_mutex_unlock(&g_process.mutex);
 }
 
+static int device_ready(QZSTD_State_T *s);
+static int ra_limit(void);
+static int ra_helper_ready(QZSTD_State_T *s);
+
 void *QZSTD_createSeqProdState(void)
 {
     QZSTD_State_T *s = (QZSTD_State_T *)calloc(1, sizeof(QZSTD_State_T));
-    if (s) s->device = -1;
+    if (s) {
+        s->device = -1;
+        /* With the device already started the state takes its engine now (a stream, events, scratch: tens of
+         * milliseconds that would otherwise sit inside the first block's latency); otherwise on the first block, like the
+         * reference's session setup (/root/reference/src/qatseqprod.c:1193-1201).  Failure here is not an error. */
+        if (g_process.status == QZSTD_OK && device_ready(s) == 0 && ra_limit() >= 2) {
+            void *slots;            /* ... and the read-ahead buffers with it: allocations stall every stream of the device */
+            (void)b200sp_stage_reserve(s->engine, QZSTD_RA_MAX, &slots);
+            /* the helper thread and its engine as well; wait until it stands (or has given up) */
+            if (ra_helper_ready(s)) {
+                pthread_mutex_lock(&s->raMu);
+                while (!s->raReady && !s->raFailed) pthread_cond_wait(&s->raCv, &s->raMu);
+                pthread_mutex_unlock(&s->raMu);
+            }
+        }
+    }
     return (void *)s;
 }
+
+static void ra_shutdown(QZSTD_State_T *s);          /* read-ahead helper thread + its engine, further down */
 
 void QZSTD_freeSeqProdState(void *sequenceProducerState)
 {
     QZSTD_State_T *s = (QZSTD_State_T *)sequenceProducerState;
     if (s) {
+        ra_shutdown(s);
         if (s->engine) {
             b200sp_engine_destroy(s->engine);
             s->engine = NULL;
@@ -456,7 +524,10 @@ static int device_ready(QZSTD_State_T *s)
             QZSTD_LOG(1, "Failed to grab an engine: all %d are taken\n", g_process.maxEngines);
             return -1;
         }
-        if (b200sp_engine_create(g_process.devices[slot], &s->engine) != B200SP_OK) {
+        const double tCreate = log_level() >= 3 ? ra_now() : 0.0;
+        const int created = b200sp_engine_create(g_process.devices[slot], &s->engine);
+        QZSTD_LOG(3, "engine created in %.1f ms\n", 1e3 * (ra_now() - tCreate));
+        if (created != B200SP_OK) {
             QZSTD_LOG(1, "Failed to create engine: %s\n", b200sp_error_string());
             pthread_mutex_lock(&g_process.mutex);
             g_process.engines--;
@@ -466,6 +537,240 @@ static int device_ready(QZSTD_State_T *s)
         }
         s->device = slot;
     }
+    return 0;
+}
+
+/* ---- transparent read-ahead -------------------------------------------------------------------------------
+ * libzstd hands the producer one block per call, and one block is one CTA for most of a millisecond: slower than
+ * software.  Applications mostly walk a buffer front to back - ZSTD_compress2 over a large buffer, or a loop
+ * over chunks like the reference's benchmark (/root/reference/test/benchmark.c:300-321) - so when a call starts
+ * where the previous one ended, the plugin reads AHEAD of the application: it copies the bytes that follow the
+ * block (as far as they are readable) into the engine's pinned staging, parses them as one GPU batch, and serves the
+ * following calls from that batch.  Two things keep this invisible:
+ *   - the copy is made with process_vm_readv on the process itself, which stops at the first unreadable page
+ *     instead of faulting, so reading past the end of the caller's buffer is harmless;
+ *   - a block is only served from the batch when the caller's bytes still equal the copy (memcmp): blocks are
+ *     parsed independently, so equal bytes mean valid sequences, and anything else (a buffer refilled in the
+ *     meantime, a shorter last block) is a miss that takes the single-block path.
+ * QZSTD_LOOKAHEAD=0 turns it off; QZSTD_LOOKAHEAD=n bounds the window to n blocks (default and maximum 64). */
+static int ra_limit(void)
+{
+    static int limit = -1;
+    if (limit < 0) {
+        const char *e = getenv("QZSTD_LOOKAHEAD");
+        int v = (e && *e) ? atoi(e) : QZSTD_RA_MAX;
+        limit = v < 0 ? 0 : v > QZSTD_RA_MAX ? QZSTD_RA_MAX : v;
+    }
+    return limit;
+}
+
+
+static int g_raBroken = 0;          /* process_vm_readv refused (seccomp / ptrace policy): never tried again */
+
+/* Serves block `src` from window w, if it is there and unchanged.  Returns 1 and *rc on a hit, *last = it was the
+ * window's last block, *k = its index. */
+static int ra_serve(QZSTD_Window *w, const unsigned char *src, size_t srcSize, int level,
+                    ZSTD_Sequence *out, size_t cap, size_t *rc, size_t *kOut)
+{
+    size_t k;
+    if (!w->base || level != w->level || src < w->base) return 0;
+    if ((size_t)(src - w->base) % w->block != 0) return 0;
+    k = (size_t)(src - w->base) / w->block;
+    if (k >= w->blocks || w->sizes[k] != srcSize) return 0;
+    if (memcmp(src, w->slots + k * (size_t)B200SP_BLOCK_MAX, srcSize) != 0) return 0;
+    *rc = w->batch.counts[k];
+    *kOut = k;
+    if (*rc >= cap - 1) { *rc = ZSTD_SEQUENCE_PRODUCER_ERROR; return 1; }   /* same guard as the reference (:1318-1322) */
+    b200sp_expand(w->batch.packed + w->batch.offsets[k], *rc, (b200sp_sequence *)out);
+    return 1;
+}
+
+/* Reads `want` blocks of `srcSize` bytes ahead from `src` into the engine's pinned staging (as far as they are
+ * readable) and parses them.  Returns 1 when a window of at least two blocks is in place.  Runs on the caller's
+ * thread (first window of a run) or on the state's helper thread (every further one). */
+static int ra_fill(QZSTD_Window *w, b200sp_engine *engine, const unsigned char *src, size_t srcSize, int level, uint32_t want)
+{
+    struct iovec local[QZSTD_RA_MAX], remote;
+    void *slots = NULL;
+    ssize_t got;
+    uint32_t n, i;
+    double t0 = 0.0, t1 = 0.0;
+    w->base = NULL;
+    if (want < 2 || g_raBroken || !engine) return 0;
+    if (b200sp_stage_reserve(engine, QZSTD_RA_MAX, &slots) != B200SP_OK) return 0;
+    for (i = 0; i < want; i++) {
+        local[i].iov_base = (unsigned char *)slots + (size_t)i * B200SP_BLOCK_MAX;
+        local[i].iov_len = srcSize;
+    }
+    remote.iov_base = (void *)src;
+    remote.iov_len = (size_t)want * srcSize;
+    if (log_level() >= 3) t0 = ra_now();
+    got = process_vm_readv(getpid(), local, want, &remote, 1, 0);
+    if (log_level() >= 3) t1 = ra_now();
+    if (got < (ssize_t)srcSize) {
+        if (got < 0 && src != NULL && errno != EFAULT) { g_raBroken = 1; QZSTD_LOG(1, "read-ahead disabled: process_vm_readv refused\n"); }
+        return 0;
+    }
+    n = (uint32_t)((size_t)got / srcSize);
+    for (i = 0; i < n; i++) w->sizes[i] = (uint32_t)srcSize;
+    if ((size_t)got % srcSize != 0 && n < want) w->sizes[n++] = (uint32_t)((size_t)got % srcSize);   /* what is readable of the last one */
+    if (n < 2) return 0;
+    if (b200sp_parse_staged(engine, w->sizes, n, level, &w->batch) != B200SP_OK || w->batch.nBlocks != n) {
+        QZSTD_LOG(1, "Read-ahead parse failed: %s\n", b200sp_error_string());
+        return 0;
+    }
+    QZSTD_LOG(3, "read-ahead: %u blocks, copy %.3f ms, parse %.3f ms\n", n, 1e3 * (t1 - t0), 1e3 * (ra_now() - t1));
+    w->slots = (unsigned char *)slots;
+    w->block = srcSize;
+    w->blocks = n;
+    w->want = want;
+    w->level = level;
+    w->base = src;
+    return 1;
+}
+
+static uint32_t ra_window_blocks(unsigned int streak)
+{
+    /* the window grows with the length of the sequential run, like a file system's read-ahead */
+    uint32_t want = streak < 2 ? 8u : streak < 12 ? 24u : (uint32_t)QZSTD_RA_MAX;
+    const int limit = ra_limit();
+    return want > (uint32_t)limit ? (uint32_t)limit : want;
+}
+
+static void *ra_helper(void *arg)
+{
+    QZSTD_State_T *s = (QZSTD_State_T *)arg;
+    /* the second engine is created here, not on the caller's thread: a stream, scratch and pinned buffers take
+     * tens of milliseconds; a request posted meanwhile waits, and fails cleanly (no window) without an engine */
+    {
+        const double t0 = ra_now();
+        void *slots;
+        if (b200sp_engine_create(b200sp_engine_device(s->engine), &s->engine2) != B200SP_OK) s->engine2 = NULL;
+        else (void)b200sp_stage_reserve(s->engine2, QZSTD_RA_MAX, &slots);
+        QZSTD_LOG(3, "helper engine created in %.1f ms\n", 1e3 * (ra_now() - t0));
+    }
+    pthread_mutex_lock(&s->raMu);
+    s->raReady = s->engine2 != NULL;
+    s->raFailed = s->engine2 == NULL;
+    pthread_cond_broadcast(&s->raCv);
+    for (;;) {
+        while (!s->raQuit && !(s->raBusy && s->raReqSrc)) pthread_cond_wait(&s->raCv, &s->raMu);
+        if (s->raQuit) break;
+        {
+            const unsigned char *src = s->raReqSrc;
+            const size_t size = s->raReqSize;
+            const int level = s->raReqLevel, wi = s->raReqWin;
+            const uint32_t want = s->raReqWant;
+            s->raReqSrc = NULL;
+            pthread_mutex_unlock(&s->raMu);
+            ra_fill(&s->win[wi], wi ? s->engine2 : s->engine, src, size, level, want);
+            pthread_mutex_lock(&s->raMu);
+        }
+        s->raBusy = 0;
+        pthread_cond_broadcast(&s->raCv);
+    }
+    pthread_mutex_unlock(&s->raMu);
+    return NULL;
+}
+
+/* Waits until the helper thread is idle: before the caller's thread touches either engine. */
+static void ra_quiesce(QZSTD_State_T *s)
+{
+    if (s->raThreadUp != 1) return;
+    pthread_mutex_lock(&s->raMu);
+    while (s->raBusy) pthread_cond_wait(&s->raCv, &s->raMu);
+    pthread_mutex_unlock(&s->raMu);
+}
+
+/* Starts the helper thread and its engine on first use.  Returns 1 when prefetching is possible. */
+static int ra_helper_ready(QZSTD_State_T *s)
+{
+    if (s->raThreadUp) return s->raThreadUp == 1;
+    s->raThreadUp = -1;
+    /* the helper's engine is an internal resource of its state: it does not count against the engine pool */
+    pthread_mutex_init(&s->raMu, NULL);
+    pthread_cond_init(&s->raCv, NULL);
+    if (pthread_create(&s->raThread, NULL, ra_helper, s) != 0) return 0;
+    s->raThreadUp = 1;
+    return 1;
+}
+
+static void ra_post(QZSTD_State_T *s, int wi, const unsigned char *src, size_t size, int level, uint32_t want)
+{
+    pthread_mutex_lock(&s->raMu);
+    s->win[wi].base = NULL;
+    s->raReqSrc = src; s->raReqSize = size; s->raReqLevel = level; s->raReqWin = wi; s->raReqWant = want;
+    s->raBusy = 1;
+    pthread_cond_broadcast(&s->raCv);
+    pthread_mutex_unlock(&s->raMu);
+}
+
+static void ra_shutdown(QZSTD_State_T *s)
+{
+    if (s->raThreadUp == 1) {
+        pthread_mutex_lock(&s->raMu);
+        s->raQuit = 1;
+        pthread_cond_broadcast(&s->raCv);
+        pthread_mutex_unlock(&s->raMu);
+        pthread_join(s->raThread, NULL);
+        pthread_mutex_destroy(&s->raMu);
+        pthread_cond_destroy(&s->raCv);
+        s->raThreadUp = 0;
+    }
+    if (s->engine2) {
+        b200sp_engine_destroy(s->engine2);
+        s->engine2 = NULL;
+    }
+}
+
+/* A window has just become current: if it was filled completely (the buffer goes on), have the helper fetch the one
+ * after it while this one is served - libzstd's entropy stage takes ~150 us per block, a window of 128 blocks is
+ * fetched and parsed in 5 ms. */
+static void ra_prefetch_next(QZSTD_State_T *s, int level)
+{
+    const QZSTD_Window *w = &s->win[s->cur];
+    if (w->base && w->blocks == w->want && !s->raBusy && ra_helper_ready(s) && s->raReady)
+        ra_post(s, s->cur ^ 1, w->base + (size_t)w->blocks * w->block, w->block, level, ra_window_blocks(s->streak + w->blocks));
+}
+
+/* The read-ahead step of the producer.  Returns 1 when the block was served (*rc), 0 when the caller goes on to the
+ * single-block path.  On return 0 the helper is idle and no window is kept. */
+static int read_ahead(QZSTD_State_T *s, const unsigned char *p, size_t srcSize, int level,
+                      ZSTD_Sequence *out, size_t cap, size_t *rc)
+{
+    const int sequential = s->lastSrc && p == s->lastSrc + s->lastSize && srcSize == s->lastSize;
+    QZSTD_Window *w = &s->win[s->cur];
+    size_t k = 0;
+    s->streak = sequential ? s->streak + 1 : 0;
+    s->lastSrc = p;
+    s->lastSize = srcSize;
+    if (ra_limit() < 2) return 0;
+    /* 1. the window being served */
+    if (ra_serve(w, p, srcSize, level, out, cap, rc, &k)) {
+        if (k + 1 == w->blocks) w->base = NULL;
+        return 1;
+    }
+    /* 2. the window the helper has been filling */
+    ra_quiesce(s);
+    w->base = NULL;
+    if (ra_serve(&s->win[s->cur ^ 1], p, srcSize, level, out, cap, rc, &k)) {
+        s->cur ^= 1;
+        s->prefetched++;
+        ra_prefetch_next(s, level);
+        if (k + 1 == s->win[s->cur].blocks) s->win[s->cur].base = NULL;
+        return 1;
+    }
+    s->win[s->cur ^ 1].base = NULL;
+    /* 3. a sequential run without a window: read ahead now, on this thread */
+    s->cur = 0;
+    if (sequential && srcSize >= 4 * KB && ra_fill(&s->win[0], s->engine, p, srcSize, level, ra_window_blocks(s->streak))) {
+        s->batchLevel = 0;          /* the engine's result buffers were reused */
+        if (ra_serve(&s->win[0], p, srcSize, level, out, cap, rc, &k)) {
+            ra_prefetch_next(s, level);
+            return 1;
+        }
+    }
+    s->win[0].base = NULL;
     return 0;
 }
 
@@ -499,6 +804,7 @@ size_t qatSequenceProducer(
     if (device_ready(s) != 0) return producer_error(s);
 
     /* look-ahead: serve the block from (or first build) the batch over the hinted buffer */
+    if (s->hintSrc) ra_quiesce(s);      /* the helper thread may be using the engine */
     {
         const unsigned char *p = (const unsigned char *)src;
         if (s->hintSrc && p >= s->hintSrc && p + srcSize <= s->hintSrc + s->hintSize &&
@@ -521,6 +827,7 @@ size_t qatSequenceProducer(
                     }
                     s->batchLevel = compressionLevel;
                     s->served = 0;
+                    s->win[0].base = NULL;
                 }
                 if (idx < s->batch.nBlocks) {
                     rc = s->batch.counts[idx];
@@ -533,6 +840,14 @@ size_t qatSequenceProducer(
                 }
             }
         }
+    }
+
+    /* transparent read-ahead: a call that continues the previous one is served from (or first builds) a window of
+     * the blocks that follow in the caller's memory */
+    if (!g_coEnabled && read_ahead(s, (const unsigned char *)src, srcSize, compressionLevel, outSeqs, outSeqsCapacity, &rc)) {
+        if (rc == ZSTD_SEQUENCE_PRODUCER_ERROR) return producer_error(s);
+        s->batched++;
+        return rc;
     }
 
     /* many threads, one block each: let the device's dispatcher batch them (optional) */
@@ -551,6 +866,7 @@ size_t qatSequenceProducer(
             return producer_error(s);
         }
         s->batchLevel = 0;          /* the engine's result buffers were reused */
+        s->win[0].base = NULL;
         rc = one.counts[0];
         if (rc >= outSeqsCapacity - 1) {        /* same guard as the reference (:1318-1322) */
             QZSTD_LOG(1, "Sequence count exceeds capacity\n");
@@ -578,6 +894,7 @@ size_t QZSTD_generateSequences(void *sequenceProducerState, ZSTD_Sequence *outSe
         return producer_error(s);
     }
     if (device_ready(s) != 0) return producer_error(s);
+    ra_quiesce(s);                  /* the helper thread may be using the engine */
 
     /* the device gathers every block's entries into ONE dense ZSTD_Sequence array, each block ending with its
      * {0, trailing literals, 0} entry, and it lands in outSeqs directly (what QZSTD_decLz4s leaves there,
@@ -588,6 +905,7 @@ size_t QZSTD_generateSequences(void *sequenceProducerState, ZSTD_Sequence *outSe
         return producer_error(s);
     }
     s->batchLevel = 0;              /* the engine's result buffers were reused */
+    s->win[0].base = NULL;
     s->batched += (srcSize + blockSize - 1) / blockSize;
     return total;
 }

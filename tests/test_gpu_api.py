@@ -203,3 +203,57 @@ def test_states_are_dealt_devices_round_robin_and_pool_is_bounded(pkg, monkeypat
         q.stopQatDevice()
         monkeypatch.delenv("QZSTD_MAX_ENGINES")
         q.startQatDevice(); q.stopQatDevice()
+
+
+def test_transparent_read_ahead(pkg, oracle):
+    """No hint, the stock six symbols only: calls that walk a buffer front to back are served from a window the plugin
+    read ahead (process_vm_readv + one GPU batch), with sequences identical to the single-block path; bytes that
+    changed after they were read ahead are never served from the window (memcmp), and a buffer that ends inside the
+    window (the page after it is unreadable) is handled."""
+    import mmap
+    q = pkg.QatSeqProd
+    q.stopQatDevice()
+    assert q.startQatDevice() == pkg.QZSTD_OK
+    E = pkg.ZSTD_SEQUENCE_PRODUCER_ERROR
+    nblk = 40
+    data = datagen.mixed_corpus(nblk * BLOCK + 70001, seed=97)
+    # the buffer ends exactly at the end of a mapping: whatever follows is not ours to read
+    mm = mmap.mmap(-1, (len(data) + 4095) // 4096 * 4096)
+    pad = len(mm) - len(data)
+    mm[pad:] = data
+    buf = np.frombuffer(mm, dtype=np.uint8)[pad:]
+    out = np.zeros((43691, 4), np.uint32)
+
+    def walk(st, level=3):
+        seqs = []
+        for b in range(nblk + 1):
+            n = min(BLOCK, len(data) - b * BLOCK)
+            rc = q.qatSequenceProducer(st, out.ctypes.data, 43691, buf.ctypes.data + b * BLOCK, n, None, 0, level, 1 << 17)
+            assert rc != E, b
+            seqs.append(out[:rc].copy())
+        return seqs
+
+    st1 = q.createSeqProdState()
+    try:
+        # reference run on the single-block path: the model is the judge, block by block
+        want = [oracle.model_block(data[b * BLOCK:(b + 1) * BLOCK], 3) for b in range(nblk + 1)]
+        got = walk(st1)
+        stats = q.getStats(st1)
+        assert stats["batched"] >= nblk - 2, stats           # everything but the first blocks came from windows
+        for b in range(nblk + 1):
+            assert got[b].shape == want[b].shape and (got[b] == want[b]).all(), f"block {b}"
+        # through libzstd: one frame over the whole buffer, no hint
+        r = oracle.compress_with_producer(buf, q.producer, st1, chunk=len(data), level=3)
+        assert r["round_trip"] and r["errors"] == 0
+        # bytes changed after they were read ahead: the window must not be served for them
+        q.qatSequenceProducer(st1, out.ctypes.data, 43691, buf.ctypes.data, BLOCK, None, 0, 3, 1 << 17)
+        q.qatSequenceProducer(st1, out.ctypes.data, 43691, buf.ctypes.data + BLOCK, BLOCK, None, 0, 3, 1 << 17)   # window built here
+        fresh = np.frombuffer(datagen.text_like(BLOCK, 77), dtype=np.uint8)
+        buf[2 * BLOCK:3 * BLOCK] = fresh
+        rc = q.qatSequenceProducer(st1, out.ctypes.data, 43691, buf.ctypes.data + 2 * BLOCK, BLOCK, None, 0, 3, 1 << 17)
+        assert rc != E and oracle.validate(fresh.tobytes(), out[:rc]) == 0
+        w = oracle.model_block(fresh.tobytes(), 3)
+        assert out[:rc].shape == w.shape and (out[:rc] == w).all()
+    finally:
+        q.freeSeqProdState(st1)
+        q.stopQatDevice()
