@@ -152,6 +152,41 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def drop_in_tool(data, level):
+    """The unmodified drop-in path, measured the way the reference measures itself: tools/qzstd_benchmark (the mirror of
+    /root/reference/test/benchmark.c: every 128 KiB chunk its own ZSTD_compress2 frame, private CCtx + state per thread,
+    no hint, no additive call) in plugin mode and in software mode, same thread count, on a 32 MB stride sample."""
+    import re
+    import tempfile
+    tool = os.path.join(ROOT, "tools", "qzstd_benchmark")
+    if not os.path.exists(tool):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tools")], check=False)
+    if not os.path.exists(tool):
+        return {"unavailable": "tools/qzstd_benchmark not built"}
+    threads = min(16, os.cpu_count() or 1)
+    sub = b"".join(data[o:o + BLOCK] for o in range(0, len(data), 6 * BLOCK))[:32 << 20]
+    out = {"threads": threads, "sample_bytes": len(sub), "loops": 5,
+           "tool": f"tools/qzstd_benchmark -t{threads} -l5 -c128K -L{level} -E1 (no -B: the stock six-symbol path)"}
+    with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+        f.write(sub)
+        f.flush()
+        for mode, key in ((0, "software_MBps"), (1, "plugin_MBps")):
+            try:
+                r = subprocess.run([tool, f"-m{mode}", f"-t{threads}", "-l5", "-c128K", f"-L{level}", "-E1", f.name],
+                                   capture_output=True, text=True, timeout=240)
+                m = re.search(r"Total: \d+ thread\(s\), (\d+) MB/s aggregate.*software fallbacks: (\d+), (PASS|FAIL)", r.stdout + r.stderr)
+                out[key] = int(m.group(1)) if m else None
+                if mode == 1 and m:
+                    out["plugin_fallbacks"] = int(m.group(2))
+                    out["plugin_round_trip"] = m.group(3) == "PASS"
+            except Exception as ex:                                     # the figure is informative; never fail the bench on it
+                out[key] = None
+                out["error"] = str(ex)[:200]
+    if out.get("software_MBps") and out.get("plugin_MBps"):
+        out["plugin_over_software"] = round(out["plugin_MBps"] / out["software_MBps"], 3)
+    return out
+
+
 def run_reference(args, rank):
     """Reference arm: the software sequence producer of stock libzstd on all host cores."""
     if rank != 0:
@@ -343,6 +378,21 @@ def main():
         q.hintSource(st, 0, 0, 0)
         extra["callbacks"] = {"value": round(unit_bytes / min(t_cb) / 1e9, 3), "unit": "GB/s",
                               "api": "QZSTD_hintSource + qatSequenceProducer per 128 KiB block (one thread; first call parses the batch)"}
+        # the same WITHOUT the hint: the unmodified six-symbol surface; the plugin notices the sequential walk and reads ahead
+        # (windows of up to 64 blocks, next window prefetched by the state's helper thread)
+        st2 = q.createSeqProdState()
+        t_nh = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            for b in range(unit_blocks):
+                n = prod(st2, sp, 43691, hp + b * BLOCK, int(sizes_h[b]), None, 0, args.level, 1 << 17)
+                assert n != ERR
+            t_nh.append(time.perf_counter() - t0)
+        nh_stats = q.getStats(st2)
+        q.freeSeqProdState(st2)
+        extra["callbacks_no_hint"] = {"value": round(unit_bytes / min(t_nh) / 1e9, 3), "unit": "GB/s",
+                                      "served_from_read_ahead": int(nh_stats["batched"]), "calls": int(nh_stats["calls"]),
+                                      "api": "qatSequenceProducer per 128 KiB block, no hint, one thread (transparent read-ahead)"}
         # the layer under the plugin: packed 8-byte wire format on the host
         eng.parse_host(hp, unit_bytes, BLOCK, args.level)
         t0 = time.perf_counter()
@@ -473,6 +523,8 @@ def main():
                 line["ratio"]["delta_per_kind"] = per_kind
         q.freeSeqProdState(st)
     q.stopQatDevice()
+    if world == 1 and not args.no_ratio:
+        line["drop_in"] = drop_in_tool(data, args.level)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
