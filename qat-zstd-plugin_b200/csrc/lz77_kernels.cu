@@ -178,7 +178,7 @@ struct Shared {         // 32-bit shared-window addresses
     uint32_t in;        // the staged block (+ pad)
     uint32_t tab;       // u32[kBuckets]        phase A: histogram; then {segment start / 8 : 15 | entries so far : 17}
     uint32_t bitmap;    // kBitmapBits bits     phase A only: overlays the spare table and the rings
-    uint32_t ringH;     // u32[2][kWindow]      H -> T: {valid:1 | lanes in the bucket - 1:5 | first such lane:5 | earlier such lanes:5 | bucket:13}
+    uint32_t ringH;     // u32[2][kWindow]      H -> T: {first lane of its bucket:1 | lanes in the bucket:6 | first such lane:5 | earlier such lanes:5 | bucket:13}, 0 = invalid
     uint32_t ringT;     // u16[2][kWindow]      H -> T: tag (in the spare table)
     uint32_t ringC;     // u32[kRingC][kWindow] {slot in the sorted table:18 | insertion index (capped):14} (T) -> packed prefix maxima (E)
     uint32_t ringL;     // u32[2][kWindow]      P1 -> P2: memoised decisions {end:9 | take lane:5 | offset:17}
@@ -225,11 +225,13 @@ __device__ __forceinline__ HashState hash_begin(const Shared &S, uint32_t w, uin
 __device__ __forceinline__ void hash_finish(const Shared &S, uint32_t w, uint32_t group, uint32_t lane, uint32_t nh, const HashState &h)
 {
     // everything the table warp needs, so that it has as few instructions of its own as possible:
-    // {valid:1 | lanes in the bucket - 1 : 5 | their first lane : 5 | earlier lanes in the bucket : 5 | bucket : 13}
+    // {first lane of its bucket:1 (bit 29) | lanes in the bucket:6 (23..28) | their first lane:5 | earlier lanes in the
+    //  bucket:5 | bucket:13}; 0 = no valid position here
     const uint32_t p = w * kWindow + group * 32u + lane;
     const uint32_t ltMask = (1u << lane) - 1u;
-    const uint32_t word = (h.v >> (32 - kBucketBits)) | (__popc(h.m & ltMask) << 13) | ((__ffs(h.m) - 1) << 18) |
-                          ((__popc(h.m) - 1) << 23) | (1u << 28);
+    const uint32_t first = __ffs(h.m) - 1;
+    const uint32_t word = (h.v >> (32 - kBucketBits)) | (__popc(h.m & ltMask) << 13) | (first << 18) |
+                          (__popc(h.m) << 23) | (first == lane ? 1u << 29 : 0u);
     const uint32_t rb = ring_byte(group, lane);
     sts32(S.ringH + (w & 1u) * (kWindow * 4u) + rb, p < nh ? word : 0u);
     sts16(S.ringT + (w & 1u) * (kWindow * 2u) + (rb >> 1), (h.v >> 4) & 0x7FFFu);
@@ -280,13 +282,12 @@ __device__ __forceinline__ void stage_table(const Shared &S, uint32_t w, uint32_
                 "mov.u32 %0, 0;\n\t"
                 "@q atom.shared.add.u32 %0, [%1], %2;\n\t}"
                 : "=r"(old[k])
-                : "r"(S.tab + (hw[k] & (kBuckets - 1u)) * 4u), "r"(((hw[k] >> 23) & 31u) + 1u),
-                  "r"(static_cast<uint32_t>((hw[k] >> 28) != 0u && ((hw[k] >> 18) & 31u) == lane))
+                : "r"(S.tab + (hw[k] & (kBuckets - 1u)) * 4u), "r"((hw[k] >> 23) & 63u), "r"(hw[k] & (1u << 29))
                 : "memory");
         }
 #pragma unroll
         for (uint32_t k = 0; k < kTUnroll; k++) {
-            const bool valid = (hw[k] >> 28) != 0u;
+            const bool valid = hw[k] != 0u;
             const uint32_t e = __shfl_sync(0xFFFFFFFFu, old[k], (hw[k] >> 18) & 31u);
             const uint32_t idx = (e & 0x1FFFFu) + ((hw[k] >> 13) & 31u);
             const uint32_t slot = (e >> 17) * kSegAlign + idx;

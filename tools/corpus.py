@@ -7,8 +7,8 @@ the label travels with every number:
   1. ``$SILESIA``  — a file (tar / concatenation) or a directory of the 12 Silesia files: label "silesia".
   2. image corpus  — a deterministic, Silesia-sized mix of REAL files that ship in this container
      image (identical on the build box and on every GPU box): source text, C headers, shared
-     objects, JSON/XML, word lists, bytecode and already-compressed images, in proportions close to
-     Silesia's text / executable / database / markup / incompressible split.
+     objects, JSON/XML, word lists and tables, in proportions close to Silesia's text / executable /
+     database / markup split (no category that differs between boxes: the image files under site-packages did).
      Label "silesia-like image corpus (real files from the container image)".
   3. synthetic     — tests/datagen.mixed_corpus, label "silesia-like synthetic".
 
@@ -39,7 +39,6 @@ _PLAN = [
     ("wordlist", "/opt/prime-rl/deps/research-environments/environments/logic_env/logic_env/games/tasks/word_sorting/scripts", (".txt",), 4_300_000),
     ("unicode-tables", "/usr/share/perl/5.38.2", (".txt", ".pl", ".pm"), 6_000_000),
     ("numeric-tables", f"{_SP}/scipy", (".npy", ".npz", ".mat", ".dat", ".csv"), 6_000_000),
-    ("compressed-images", f"{_SP}", (".png", ".jpg", ".gz"), 6_000_000),
     ("python-source", f"{_SP}/scipy", (".py",), 40_000_000),
 ]
 _FILE_CAP = 4 << 20
@@ -92,7 +91,7 @@ def load(target: int = SILESIA_BYTES, allow_image: bool = True):
             data = open(env, "rb").read()
         return data, "silesia", {"source": env, "bytes": len(data)}
     if allow_image:
-        cache = f"/tmp/b200sp_image_corpus_{target}.bin"
+        cache = f"/tmp/b200sp_image_corpus_v2_{target}.bin"
         if os.path.exists(cache) and os.path.getsize(cache) >= int(0.9 * target):
             data = open(cache, "rb").read()
             return data, "silesia-like image corpus (real files from the container image)", \

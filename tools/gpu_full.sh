@@ -9,4 +9,5 @@ timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/$
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 1 --no-sweep --no-ratio --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lz77 -s 2 -c 1 -f -o gpurun_out/prof_${TAG}_L3 python tools/ncu_one.py 3 0 1617 > gpurun_out/${TAG}_ncu_L3.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lz77 -s 2 -c 1 -f -o gpurun_out/prof_${TAG}_L6 python tools/ncu_one.py 6 0 296 > gpurun_out/${TAG}_ncu_L6.log 2>&1
+python tools/corpus_parts.py > gpurun_out/${TAG}_corpus_parts.txt 2>&1
 ls -la gpurun_out | grep ${TAG}
