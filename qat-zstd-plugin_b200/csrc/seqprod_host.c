@@ -39,6 +39,7 @@
 
 #define QZSTD_MAX_DEVICES 16
 #define QZSTD_RA_MAX      64         /* blocks read ahead at most (8 MiB) */
+#define QZSTD_EAGER_STATES 64        /* states whose read-ahead buffers (~240 MB of device memory each) are stood up at creation; later ones on first use */
 
 typedef struct {
     int status;                 /* QZSTD_FAIL / QZSTD_STARTED / QZSTD_OK */
@@ -205,7 +206,7 @@ void *QZSTD_createSeqProdState(void)
         /* With the device already started the state takes its engine now (a stream, events, scratch: tens of
          * milliseconds that would otherwise sit inside the first block's latency); otherwise on the first block, like the
          * reference's session setup (/root/reference/src/qatseqprod.c:1193-1201).  Failure here is not an error. */
-        if (g_process.status == QZSTD_OK && device_ready(s) == 0 && ra_limit() >= 2) {
+        if (g_process.status == QZSTD_OK && device_ready(s) == 0 && ra_limit() >= 2 && g_process.engines <= QZSTD_EAGER_STATES) {
             void *slots;            /* ... and the read-ahead buffers with it: allocations stall every stream of the device */
             (void)b200sp_stage_reserve(s->engine, QZSTD_RA_MAX, &slots);
             /* the helper thread and its engine as well; wait until it stands (or has given up) */
