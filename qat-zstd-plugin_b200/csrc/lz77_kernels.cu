@@ -1068,8 +1068,15 @@ __device__ __forceinline__ void stage_rep_parse(const Shared &S, uint32_t w, uin
         chain = false;
         if (!isRep) {
             if (ml >= extCap) ml = coop_len(in, start, off, ml, n, lane);          // cut by the cap: extend
-            if (start > anchor) {
-                // catch up to the left: lane k tests byte start - k (k = 1..31)
+            // catch up to the left.  Usually the byte before the match already differs (the search at start - 1 would have
+            // found the longer match): one uniform byte compare settles that before the warp-wide test
+            bool grow = start > anchor && start > off;
+            if (grow) {
+                const uint32_t x = start - 1u, y = start - 1u - off;
+                grow = ((ldsc32(in + (x & ~3u)) >> ((x & 3u) * 8u)) & 0xFFu) == ((ldsc32(in + (y & ~3u)) >> ((y & 3u) * 8u)) & 0xFFu);
+            }
+            if (grow) {
+                // lane k tests byte start - k (k = 1..31)
                 const bool ok = lane >= 1u && start >= anchor + lane && start >= off + lane &&
                                 ((ldsc32(in + ((start - lane) & ~3u)) >> (((start - lane) & 3u) * 8u)) & 0xFFu) ==
                                 ((ldsc32(in + ((start - lane - off) & ~3u)) >> (((start - lane - off) & 3u) * 8u)) & 0xFFu);

@@ -254,6 +254,18 @@ def test_transparent_read_ahead(pkg, oracle):
         assert rc != E and oracle.validate(fresh.tobytes(), out[:rc]) == 0
         w = oracle.model_block(fresh.tobytes(), 3)
         assert out[:rc].shape == w.shape and (out[:rc] == w).all()
+        # smaller chunks (32 KiB each its own call), another level, a walk that jumps back in the middle
+        st2 = q.createSeqProdState()
+        small = 32768
+        order = list(range(0, 30)) + list(range(10, 45))
+        for b in order:
+            blk = buf[b * small:(b + 1) * small].tobytes()        # (block 2 of the buffer was rewritten above)
+            rc = q.qatSequenceProducer(st2, out.ctypes.data, 43691, buf.ctypes.data + b * small, small, None, 0, 6, 1 << 17)
+            assert rc != E
+            w = oracle.model_block(blk, 6)
+            assert out[:rc].shape == w.shape and (out[:rc] == w).all(), f"32 KiB chunk {b}"
+        assert q.getStats(st2)["batched"] >= len(order) - 6
+        q.freeSeqProdState(st2)
     finally:
         q.freeSeqProdState(st1)
         q.stopQatDevice()
