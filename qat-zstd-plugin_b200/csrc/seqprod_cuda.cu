@@ -64,7 +64,7 @@ double now_seconds()
 
 // 0 = done, 1 = timed out, otherwise the CUDA error
 // Polling discipline shared by both waits: a few dozen back-to-back queries catch short waits quickly, then the
-// thread sleeps between queries with a growing interval (20 us ... 200 us).  Every query takes a driver lock: with
+// thread sleeps between queries with a slowly growing interval (20 us ... 200 us).  Every query takes a driver lock: with
 // one or two engines per compressing thread, thousands of spinning queries slow down everybody's launches.
 struct Backoff {
     double deadline = now_seconds() + kTimeoutSeconds;
@@ -76,7 +76,7 @@ struct Backoff {
         if (now_seconds() > deadline) return true;
         timespec ts = {0, sleepNs};
         nanosleep(&ts, nullptr);
-        if (sleepNs < 200000) sleepNs += sleepNs / 2;
+        if ((polls & 7u) == 0u && sleepNs < 200000) sleepNs += sleepNs / 2;     // 20 us for the first waits of a call, 200 us after ~2 ms
         return false;
     }
 };
@@ -621,6 +621,11 @@ static int host_pipeline(b200sp_engine *e, const void *h_src, size_t srcSize, ui
     for (size_t b = 0; b < nBlocks;) {
         chunkStart[nChunks++] = b;
         b += nChunks == 1 ? first : nChunks == 2 ? sms - first : big;
+    }
+    // ... and the last one a quarter wave again: what cannot overlap anything is the fetch of the last chunk's entries
+    if (nChunks >= 2 && nChunks < kMaxChunks && nBlocks - chunkStart[nChunks - 1] > 2 * first) {
+        chunkStart[nChunks] = nBlocks - first;
+        nChunks++;
     }
     chunkStart[nChunks] = nBlocks;
 
