@@ -184,6 +184,24 @@ def drop_in_tool(data, level):
                 out["error"] = str(ex)[:200]
     if out.get("software_MBps") and out.get("plugin_MBps"):
         out["plugin_over_software"] = round(out["plugin_MBps"] / out["software_MBps"], 3)
+    # the step after the producer, multi-threaded: whole-buffer GPU sequences + ZSTD_compressSequences on
+    # `threads` host threads, parts of 64 MiB pipelined against the GPU, buffers page-locked with QZSTD_registerBuffer; the WHOLE workload, compressed once
+    hand = os.path.join(ROOT, "tools", "qzstd_handoff")
+    if os.path.exists(hand):
+        with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+            f.write(data)
+            f.flush()
+            try:
+                r = subprocess.run([hand, f"-t{threads}", "-l3", f"-L{level}", "-f8", "-p64", f.name], capture_output=True, text=True, timeout=240)
+                m = re.search(r"Hand-off: (\d+) -> (\d+) .*?: (\d+) MB/s .*?sequence production ([\d.]+) ms of ([\d.]+) ms\), (PASS|FAIL)", r.stdout)
+                if m:
+                    out["hand_off_mt"] = {"MBps": int(m.group(3)), "bytes": int(m.group(1)), "csize": int(m.group(2)),
+                                          "sequence_production_ms": float(m.group(4)), "total_ms": float(m.group(5)),
+                                          "round_trip": m.group(6) == "PASS", "threads": threads,
+                                          "tool": f"tools/qzstd_handoff -t{threads} -l3 -L{level} -f8 -p64 (QZSTD_generateSequencesIndexed + "
+                                                  "ZSTD_compressSequences per 1 MiB frame on the host threads)"}
+            except Exception as ex:
+                out["hand_off_mt"] = {"error": str(ex)[:200]}
     return out
 
 

@@ -133,6 +133,13 @@ int b200sp_stage_reserve(b200sp_engine *engine, uint32_t nSlots, void **slots);
 int b200sp_parse_staged(b200sp_engine *engine, const uint32_t *sizes, uint32_t nBlocks, int level,
                         b200sp_result *result);
 
+/* Page-locks a range of the caller's memory so that the host-path calls copy to and from it by DMA directly
+ * instead of through the engine's staging: the counterpart of the reference's SVM mode, in which the engine works
+ * on the application's buffer rather than on a USDM copy (/root/reference/src/qatseqprod.c:1222-1227).  The range
+ * must stay mapped until it is unregistered.  Returns B200SP_OK or B200SP_ECUDA. */
+int b200sp_host_register(void *ptr, size_t bytes);
+int b200sp_host_unregister(void *ptr);
+
 /* Wire format -> ZSTD_Sequence[] (rep = 0). */
 void b200sp_expand(const uint64_t *packed, size_t count, b200sp_sequence *out);
 

@@ -116,6 +116,20 @@ int QZSTD_setCoalescing(int enable);
 size_t QZSTD_generateSequences(void *sequenceProducerState, ZSTD_Sequence *outSeqs, size_t outSeqsCapacity,
                                const void *src, size_t srcSize, size_t blockSize, int compressionLevel);
 
+/* The same with an index: blockIndex[b] = position in outSeqs of block b's first entry, blockIndex[nBlocks] = the
+ * number of entries (blockIndexCapacity >= nBlocks + 1, nBlocks = ceil(srcSize / blockSize)).  With it a caller cuts
+ * the array at block boundaries without scanning it - e.g. to entropy-code ranges of blocks on several host threads,
+ * one ZSTD_compressSequences() frame per range (tools/handoff.c; SURVEY 8f-1 "multi-thread host entropy stage"). */
+size_t QZSTD_generateSequencesIndexed(void *sequenceProducerState, ZSTD_Sequence *outSeqs, size_t outSeqsCapacity,
+                                      const void *src, size_t srcSize, size_t blockSize, int compressionLevel,
+                                      size_t *blockIndex, size_t blockIndexCapacity);
+
+/* Page-locks [ptr, ptr + size) for the device (additive): QZSTD_generateSequences*() and the look-ahead hint then move
+ * the input and the ZSTD_Sequence array by DMA straight from / into the caller's memory - the counterpart of the
+ * reference's SVM mode (/root/reference/src/qatseqprod.c:1222-1227).  Returns QZSTD_OK or QZSTD_FAIL. */
+int QZSTD_registerBuffer(void *ptr, size_t size);
+int QZSTD_unregisterBuffer(void *ptr);
+
 #endif /* QATSEQPROD_H */
 
 #if defined (__cplusplus)

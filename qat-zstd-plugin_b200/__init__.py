@@ -81,6 +81,12 @@ def _load():
     l.QZSTD_getStats.restype = None
     l.QZSTD_generateSequences.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int]
     l.QZSTD_generateSequences.restype = c_size_t
+    l.QZSTD_generateSequencesIndexed.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_void_p, c_size_t]
+    l.QZSTD_generateSequencesIndexed.restype = c_size_t
+    l.QZSTD_registerBuffer.argtypes = [c_void_p, c_size_t]
+    l.QZSTD_registerBuffer.restype = c_int
+    l.QZSTD_unregisterBuffer.argtypes = [c_void_p]
+    l.QZSTD_unregisterBuffer.restype = c_int
     l.QZSTD_setCoalescing.argtypes = [c_int]
     l.QZSTD_setCoalescing.restype = c_int
     # --- b200seqprod.h
@@ -121,7 +127,8 @@ lib = _load()
 # Every symbol include/qatseqprod.h and include/b200seqprod.h declare (checked by the CPU tests).
 EXPORTED_SYMBOLS = [
     "QZSTD_version", "QZSTD_startQatDevice", "QZSTD_stopQatDevice", "QZSTD_createSeqProdState",
-    "QZSTD_freeSeqProdState", "qatSequenceProducer", "QZSTD_hintSource", "QZSTD_getStats", "QZSTD_generateSequences",
+    "QZSTD_freeSeqProdState", "qatSequenceProducer", "QZSTD_hintSource", "QZSTD_getStats", "QZSTD_generateSequences", "QZSTD_generateSequencesIndexed", "QZSTD_registerBuffer", "QZSTD_unregisterBuffer",
+    "b200sp_host_register", "b200sp_host_unregister",
     "QZSTD_setCoalescing", "b200sp_parse_blocks", "b200sp_stage_reserve", "b200sp_parse_staged",
     "b200sp_driver_device_count", "b200sp_device_count", "b200sp_warmup", "b200sp_engine_create", "b200sp_engine_destroy",
     "b200sp_engine_device", "b200sp_engine_sm_count", "b200sp_parse_device", "b200sp_sync",

@@ -966,6 +966,20 @@ int b200sp_parse_blocks(b200sp_engine *e, const void *const *h_blocks, const uin
     return b200sp_parse_staged(e, sizes, nBlocks, level, res);
 }
 
+int b200sp_host_register(void *ptr, size_t bytes)
+{
+    if (!ptr || bytes == 0) return fail(B200SP_EINVAL, "host_register: bad argument");
+    CU_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable), "cudaHostRegister");
+    return B200SP_OK;
+}
+
+int b200sp_host_unregister(void *ptr)
+{
+    if (!ptr) return fail(B200SP_EINVAL, "host_unregister: bad argument");
+    CU_TRY(cudaHostUnregister(ptr), "cudaHostUnregister");
+    return B200SP_OK;
+}
+
 void b200sp_expand(const uint64_t *packed, size_t count, b200sp_sequence *out)
 {
     for (size_t i = 0; i < count; i++) {

@@ -879,11 +879,31 @@ size_t qatSequenceProducer(
     return rc;
 }
 
+int QZSTD_registerBuffer(void *ptr, size_t size)
+{
+    if (g_process.status != QZSTD_OK) return QZSTD_FAIL;
+    return b200sp_host_register(ptr, size) == B200SP_OK ? QZSTD_OK : QZSTD_FAIL;
+}
+
+int QZSTD_unregisterBuffer(void *ptr)
+{
+    return b200sp_host_unregister(ptr) == B200SP_OK ? QZSTD_OK : QZSTD_FAIL;
+}
+
 size_t QZSTD_generateSequences(void *sequenceProducerState, ZSTD_Sequence *outSeqs, size_t outSeqsCapacity,
                                const void *src, size_t srcSize, size_t blockSize, int compressionLevel)
 {
+    return QZSTD_generateSequencesIndexed(sequenceProducerState, outSeqs, outSeqsCapacity, src, srcSize, blockSize,
+                                          compressionLevel, NULL, 0);
+}
+
+size_t QZSTD_generateSequencesIndexed(void *sequenceProducerState, ZSTD_Sequence *outSeqs, size_t outSeqsCapacity,
+                                      const void *src, size_t srcSize, size_t blockSize, int compressionLevel,
+                                      size_t *blockIndex, size_t blockIndexCapacity)
+{
     QZSTD_State_T *s = (QZSTD_State_T *)sequenceProducerState;
     size_t total = 0;
+    b200sp_result res;
 
     if (s) s->calls++;
     if (blockSize == 0) blockSize = ZSTD_BLOCKSIZE_MAX;
@@ -900,10 +920,15 @@ size_t QZSTD_generateSequences(void *sequenceProducerState, ZSTD_Sequence *outSe
     /* the device gathers every block's entries into ONE dense ZSTD_Sequence array, each block ending with its
      * {0, trailing literals, 0} entry, and it lands in outSeqs directly (what QZSTD_decLz4s leaves there,
      * :1013-1091, for all blocks at once): no per-entry work on the host */
+    if (blockIndex && blockIndexCapacity < (srcSize + blockSize - 1) / blockSize + 1) return producer_error(s);
     if (b200sp_sequences_host(s->engine, src, srcSize, (uint32_t)blockSize, compressionLevel,
-                              (b200sp_sequence *)outSeqs, outSeqsCapacity, &total, NULL) != B200SP_OK) {
+                              (b200sp_sequence *)outSeqs, outSeqsCapacity, &total, &res) != B200SP_OK) {
         QZSTD_LOG(1, "Batch parse failed: %s\n", b200sp_error_string());
         return producer_error(s);
+    }
+    if (blockIndex) {
+        uint32_t b;
+        for (b = 0; b <= res.nBlocks; b++) blockIndex[b] = (size_t)res.offsets[b];
     }
     s->batchLevel = 0;              /* the engine's result buffers were reused */
     s->win[0].base = NULL;

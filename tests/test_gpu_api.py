@@ -269,3 +269,60 @@ def test_transparent_read_ahead(pkg, oracle):
     finally:
         q.freeSeqProdState(st1)
         q.stopQatDevice()
+
+
+def test_indexed_hand_off_and_registered_buffers(pkg, oracle):
+    """QZSTD_generateSequencesIndexed: the per-block index cuts the dense array exactly at the block delimiters, so
+    ranges of blocks can be entropy-coded independently (one ZSTD_compressSequences frame per range, the multi-thread
+    hand-off of tools/handoff.c); with the caller's buffers page-locked by QZSTD_registerBuffer (the SVM analogue,
+    /root/reference/src/qatseqprod.c:1222-1227) the result is the same."""
+    q = pkg.QatSeqProd
+    assert q.startQatDevice() == pkg.QZSTD_OK
+    st = q.createSeqProdState()
+    try:
+        data = datagen.mixed_corpus(37 * BLOCK + 4242, seed=99)
+        src = np.frombuffer(bytearray(data), dtype=np.uint8)
+        nb = 38
+        cap = len(data) // 3 + 8 * nb
+        runs = []
+        for pinned in (False, True):
+            out = np.zeros((cap, 4), np.uint32)
+            index = np.zeros(nb + 1, np.uint64)
+            if pinned:
+                assert pkg.lib.QZSTD_registerBuffer(src.ctypes.data, src.size) == pkg.QZSTD_OK
+                assert pkg.lib.QZSTD_registerBuffer(out.ctypes.data, out.nbytes) == pkg.QZSTD_OK
+            n = pkg.lib.QZSTD_generateSequencesIndexed(st, out.ctypes.data, cap, src.ctypes.data, src.size, 0, 3, index.ctypes.data, nb + 1)
+            if pinned:
+                assert pkg.lib.QZSTD_unregisterBuffer(src.ctypes.data) == pkg.QZSTD_OK
+                assert pkg.lib.QZSTD_unregisterBuffer(out.ctypes.data) == pkg.QZSTD_OK
+            assert n != pkg.ZSTD_SEQUENCE_PRODUCER_ERROR and int(index[nb]) == n and int(index[0]) == 0
+            for b in (0, 1, 17, 36, 37):
+                got = out[int(index[b]):int(index[b + 1])]
+                want = oracle.model_block(data[b * BLOCK:(b + 1) * BLOCK], 3)
+                assert got.shape == want.shape and (got == want).all(), f"block {b} (pinned={pinned})"
+                assert got[-1, 0] == 0 and got[-1, 2] == 0                 # every block closes with its delimiter
+            runs.append(out[:n].copy())
+        assert runs[0].shape == runs[1].shape and (runs[0] == runs[1]).all()
+        # a range of blocks is a self-contained ZSTD_compressSequences job
+        lo, hi = 8, 16
+        part = data[lo * BLOCK:hi * BLOCK]
+        r = oracle.compress_sequences(part, runs[0][int(index[lo]):int(index[hi])], level=3)
+        assert r["round_trip"]
+        # too small an index array is refused
+        small = np.zeros(nb, np.uint64)
+        assert pkg.lib.QZSTD_generateSequencesIndexed(st, runs[0].ctypes.data, cap, src.ctypes.data, src.size, 0, 3, small.ctypes.data, nb) == pkg.ZSTD_SEQUENCE_PRODUCER_ERROR
+    finally:
+        q.freeSeqProdState(st)
+        q.stopQatDevice()
+
+
+def test_hand_off_tool_multi_thread(pkg, tmp_path):
+    """tools/qzstd_handoff: GPU sequences for the whole buffer + the entropy stage on four host threads, frames verified."""
+    import subprocess
+    tool = os.path.join(ROOT, "tools", "qzstd_handoff")
+    if not os.path.exists(tool):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tools")], check=True)
+    f = tmp_path / "in.bin"
+    f.write_bytes(datagen.mixed_corpus(70 * BLOCK + 999, seed=98))
+    r = subprocess.run([tool, "-t4", "-l2", "-L3", "-f4", "-p4", str(f)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
