@@ -18,9 +18,11 @@
  *       pool        26 warps    one queue of 52 fused tasks per stage (two per warp): task g scans the last `scan`
  *                               entries of each position's bucket for group g of window t-2 (16-byte loads of the
  *                               sorted table, tag filter, most recent first; the longest match wins - `scan` is the
- *                               level-scaled search depth), adopts the right neighbour's match when it also holds one
- *                               byte earlier, leaves the packed prefix maximum of match ends, and - hidden behind its
- *                               first loads - hashes group g of window t
+ *                               level-scaled search depth; levels 1-4 rank candidates on 16 bytes, extend the winner and
+ *                               probe the group's dominant offset, levels 5-12 measure every candidate in full, deep
+ *                               scans by the whole warp), leaves the packed prefix maximum of match ends (levels 1-4) or
+ *                               the own match of every position (levels 5-12), and - hidden behind its first loads -
+ *                               hashes group g of window t
  *       T  table    window t-1   1 warp   walks the window in order: bucket counter += multiplicity (exact serial
  *                               insertion index of every position), stores the position into its slot of the sorted
  *                               table, hands slot and index to the pool
@@ -29,6 +31,9 @@
  *                               fixed point; the entry of the second half is handed over through shared memory
  *       P2 emit     window t-4   2 warps  (one per half window) lane = group: follow the links, scans for
  *                               anchors / output slots, 16-byte ZSTD_Sequence stores; carry handed over likewise
+ *       R  rep parse window t-3  1 warp   levels 5-12 instead of P1/P2: the serial repcode-aware lazy parse
+ *                               (stage_rep_parse), warp-uniform state, lane-parallel inside a step
+ * L2 policy: the input (TMA) and the sequence stores are evict-first, the table stores evict-last.
  * The result is bit-identical to oracle/seqmodel.c (the serial statement); oracle/lanemodel.c states
  * the P1/P2 formulation lane by lane on the CPU.  Integer/indexing work only: no tensor cores, no TMEM.
  */
