@@ -984,41 +984,55 @@ __device__ __forceinline__ void stage_rep_parse(const Shared &S, uint32_t w, uin
     uint32_t ip = st.ip, anchor = st.anchor, rep1 = st.rep1, rep2 = st.rep2;
     uint32_t dec0 = 0;          // where the decision in progress started (it is taken up again from there when deferred)
     bool chain = false;         // a decision is in progress and its best so far is the own match of `ip`
+    // The span: 32 positions from sBase with their own matches and the masks that do not depend on the repeated
+    // offset (H: has a match, M1 / M2: its own-only lazy step).  It is kept while the walk stays inside it - a take
+    // usually lands a dozen positions further on - and only "the repeated offset matches here" (E) is computed again.
+    uint32_t sBase = 0, ow = 0, H = 0, M1 = 0, M2 = 0;
+    bool spanValid = false;
     while (ip < avail) {
-        // ---- a span of 32 positions from ip: own match, its price-adjusted length, "the repeated offset matches here"
-        const uint32_t p = ip + lane;
-        uint32_t ow = 0;
-        if (p < avail) {
-            const uint32_t r = p >= wBase ? p - wBase : p + kWindow - wBase;
-            ow = lds32((p >= wBase ? rowCur : rowPrev) + ring_byte(r >> 5, r & 31u));
+        if (!spanValid || ip < sBase || ip - sBase > 20u) {
+            sBase = ip;
+            spanValid = true;
+            const uint32_t p = sBase + lane;
+            ow = 0;
+            if (p < avail) {
+                const uint32_t r = p >= wBase ? p - wBase : p + kWindow - wBase;
+                ow = lds32((p >= wBase ? rowCur : rowPrev) + ring_byte(r >> 5, r & 31u));
+            }
+            const int32_t G = static_cast<int32_t>((ow >> 17) * 4u) - static_cast<int32_t>(31 - __clz((ow & 0x1FFFFu) + 1u));
+            const uint32_t ow1 = __shfl_down_sync(0xFFFFFFFFu, ow, 1), ow2 = __shfl_down_sync(0xFFFFFFFFu, ow, 2);
+            const int32_t G1 = __shfl_down_sync(0xFFFFFFFFu, G, 1), G2 = __shfl_down_sync(0xFFFFFFFFu, G, 2);
+            // the lazy step of a position whose best so far is its own match, repeated offset not involved (lanes 0..29)
+            const bool mv1 = lazyDepth >= 1u && ow1 != 0u && G1 > G + 4;
+            const bool mv2 = !mv1 && lazyDepth >= 2u && ow2 != 0u && G2 > G + 7;
+            H = __ballot_sync(0xFFFFFFFFu, ow != 0u);
+            M1 = __ballot_sync(0xFFFFFFFFu, mv1);
+            M2 = __ballot_sync(0xFFFFFFFFu, mv2);
         }
+        const uint32_t shift = ip - sBase;                  // the walk stands on lane `shift` of the span
         bool eq = false;
-        if (rep1 != 0u && p >= rep1 && p + 4u <= n) eq = ld32u(in, p) == ld32u(in, p - rep1);
-        const int32_t G = static_cast<int32_t>((ow >> 17) * 4u) - static_cast<int32_t>(31 - __clz((ow & 0x1FFFFu) + 1u));
-        const uint32_t ow1 = __shfl_down_sync(0xFFFFFFFFu, ow, 1), ow2 = __shfl_down_sync(0xFFFFFFFFu, ow, 2);
-        const int32_t G1 = __shfl_down_sync(0xFFFFFFFFu, G, 1), G2 = __shfl_down_sync(0xFFFFFFFFu, G, 2);
-        // the lazy step of a position whose best so far is its own match, repeated offset not involved (lanes 0..29)
-        const bool mv1 = lazyDepth >= 1u && ow1 != 0u && G1 > G + 4;
-        const bool mv2 = !mv1 && lazyDepth >= 2u && ow2 != 0u && G2 > G + 7;
-        const uint32_t H = __ballot_sync(0xFFFFFFFFu, ow != 0u), E = __ballot_sync(0xFFFFFFFFu, eq);
-        const uint32_t M1 = __ballot_sync(0xFFFFFFFFu, mv1), M2 = __ballot_sync(0xFFFFFFFFu, mv2);
+        {
+            const uint32_t p = sBase + lane;
+            if (rep1 != 0u && p >= rep1 && p + 4u <= n) eq = ld32u(in, p) == ld32u(in, p - rep1);
+        }
+        const uint32_t E = __ballot_sync(0xFFFFFFFFu, eq);
         const uint32_t C = H & ~(E >> 1) & ~(E >> 2);       // own match here, repeated offset silent one and two bytes on
-        const uint32_t lim = avail - ip;                    // positions of the span that are known (>= 1)
-        uint32_t s = 0;
+        const uint32_t lim = avail - sBase;                 // positions of the span that are known (>= 1)
+        uint32_t s = shift;
         if (!chain) {
             // next position at which an own match starts or the repeated offset matches one byte further on
-            uint32_t starts = (H | (E >> 1)) & 0x7FFFFFFFu;      // lane 31 cannot see the byte after the span
+            uint32_t starts = (H | (E >> 1)) & 0x7FFFFFFFu & (0xFFFFFFFFu << shift);      // lane 31 cannot see the byte after the span
             if (lim < 32u) starts &= (1u << lim) - 1u;
-            if (!starts) { ip += min(lim, 31u); continue; }
+            if (!starts) { ip = sBase + min(lim, 31u); spanValid = false; continue; }
             s = __ffs(starts) - 1;
-            dec0 = ip + s;
+            dec0 = sBase + s;
         }
         uint32_t ml = 0, off = 0, start = 0;
         bool isRep = false, done = false, defer = false;
         while (!done) {
             if (s > 29u) break;                                               // look-ahead leaves the span: move the span
             if (!last && s + lazyDepth >= lim) { defer = true; break; }        // ... or needs the next window: next stage
-            const uint32_t base = ip + s;
+            const uint32_t base = sBase + s;
             if ((C >> s) & 1u) {
                 if ((M1 >> s) & 1u) { s += 1u; chain = true; continue; }
                 if ((M2 >> s) & 1u) { s += 2u; chain = true; continue; }
@@ -1069,7 +1083,7 @@ __device__ __forceinline__ void stage_rep_parse(const Shared &S, uint32_t w, uin
             if (!moved) done = true;
         }
         if (defer) { ip = dec0; chain = false; break; }
-        if (!done) { ip += s; continue; }                                      // same decision, span moved to its base
+        if (!done) { ip = sBase + s; spanValid = false; continue; }            // same decision, span moved to its base
         chain = false;
         if (!isRep) {
             if (ml >= extCap) ml = coop_len(in, start, off, ml, n, lane);          // cut by the cap: extend
