@@ -159,7 +159,7 @@ def drop_in_tool(data, level):
     import re
     import tempfile
     tool = os.path.join(ROOT, "tools", "qzstd_benchmark")
-    if not os.path.exists(tool):
+    if not os.path.exists(tool) or not os.path.exists(os.path.join(ROOT, "tools", "qzstd_handoff")):
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tools")], check=False)
     if not os.path.exists(tool):
         return {"unavailable": "tools/qzstd_benchmark not built"}
