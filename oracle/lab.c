@@ -358,7 +358,7 @@ int main(int argc, char **argv)
     seqmodel_params_for_level(level, &g_prm);
     g_prm.keyBytes = env_int("MODEL_KEYBYTES", g_prm.keyBytes); g_prm.rank16 = env_int("MODEL_RANK16", g_prm.rank16); g_prm.scan = env_int("MODEL_SCAN", g_prm.scan);
     g_prm.lazyDepth = env_int("MODEL_LAZY", g_prm.lazyDepth); g_prm.backExt = env_int("MODEL_BACKEXT", g_prm.backExt);
-    g_prm.minMatch = env_int("MODEL_MINMATCH", g_prm.minMatch); g_prm.repParse = env_int("MODEL_REPPARSE", g_prm.repParse); g_prm.domBias = env_int("MODEL_DOMBIAS", g_prm.domBias); g_prm.extCap = env_int("MODEL_EXTCAP", g_prm.extCap);
+    g_prm.minMatch = env_int("MODEL_MINMATCH", g_prm.minMatch); g_prm.repParse = env_int("MODEL_REPPARSE", g_prm.repParse); g_prm.domBias = env_int("MODEL_DOMBIAS", g_prm.domBias); g_prm.nearN = env_int("MODEL_NEARN", g_prm.nearN); g_prm.extCap = env_int("MODEL_EXTCAP", g_prm.extCap);
     size_t calls, errs; int ok;
     size_t c = oracle_compress_with_producer(src, sz, chunk, level, lab_producer, &L, ZSTD_ps_enable, 0, 1, &calls, &errs, &ok);
     const char *base = strrchr(argv[1], '/'); base = base ? base + 1 : argv[1];

@@ -23,7 +23,7 @@ class Sequence(Structure):
 
 class ModelParams(Structure):
     _fields_ = [("keyBytes", c_int), ("scan", c_int), ("rank16", c_int), ("minMatch", c_int), ("extCap", c_int),
-                ("lazyDepth", c_int), ("window", c_int), ("backExt", c_int), ("repParse", c_int), ("domBias", c_int)]
+                ("lazyDepth", c_int), ("window", c_int), ("backExt", c_int), ("repParse", c_int), ("domBias", c_int), ("nearN", c_int)]
 
 
 def build() -> None:

@@ -58,6 +58,7 @@ void seqmodel_params_for_level(int level, SeqModelParams *prm)
     prm->backExt = level <= 4 ? 1 : 0;   /* the repcode-aware parse catches up at take time instead */
     prm->repParse = level <= 4 ? 0 : 1;
     prm->domBias = level <= 4 ? 0 : -1;  /* fast classes probe the group's dominant offset; ties go to it */
+    prm->nearN = level <= 4 ? 0 : 16;    /* levels 5-12: tags speak for the next four bytes; the 16 nearest entries are measured whatever their tag */
 }
 
 typedef struct { uint32_t end, off; } BestMatch;   /* end = p + len (0 = none) */
@@ -98,7 +99,8 @@ int seqmodel_own_matches(const uint8_t *src, size_t n, const SeqModelParams *prm
             const uint32_t lo = rd32(src + p), hi = rd32(src + p + 4);
             const uint32_t v = key_hash(lo, hi, prm->keyBytes);
             const uint32_t b = v >> (32 - SEQMODEL_BUCKET_BITS);
-            const uint32_t tag = (v >> (32 - SEQMODEL_BUCKET_BITS - SEQMODEL_TAG_BITS)) & ((1u << SEQMODEL_TAG_BITS) - 1u);
+            uint32_t tag = (v >> (32 - SEQMODEL_BUCKET_BITS - SEQMODEL_TAG_BITS)) & ((1u << SEQMODEL_TAG_BITS) - 1u);
+            if (prm->nearN > 0) tag = (hi * 0xC2B2AE3Du) >> (32 - SEQMODEL_TAG_BITS);     /* levels 5-12: the tag speaks for the NEXT four bytes */
             const uint32_t idx = count[b];                   /* entries of the bucket before p */
             sorted[start[b] + idx] = p | (tag << 17);
             count[b] = idx + 1;
@@ -107,7 +109,7 @@ int seqmodel_own_matches(const uint8_t *src, size_t n, const SeqModelParams *prm
             const uint32_t avail = idx < scan ? idx : scan;
             for (uint32_t j = 1; j <= avail; j++) {
                 const uint32_t e = sorted[start[b] + idx - j];
-                if ((e >> 17) != tag) continue;
+                if (prm->nearN > 0 ? (j > (uint32_t)prm->nearN && (e >> 17) != tag) : (e >> 17) != tag) continue;
                 const uint32_t q = e & 0x1FFFFu;
                 const uint8_t *a = src + p, *c = src + q;
                 const uint32_t stop = prm->rank16 && lim > MODEL_PROBE ? MODEL_PROBE : lim;   /* fast classes rank on 16 bytes */

@@ -43,6 +43,8 @@ typedef struct {
     int repParse;     /* 0: greedy/lazy parse over the propagated matches B (fast classes, lanemodel.c);
                          1: serial repcode-aware lazy parse over the own matches (levels 5-12, one warp per block)  */
     int domBias;      /* fast classes: >= 0 enables the dominant-offset probe; the scan's winner must be longer by more than this */
+    int nearN;        /* levels 5-12 (> 0): the entry tag is a hash of bytes 4..7, so a deep scan measures only candidates that
+                         agree on eight bytes; the nearest nearN entries are measured whatever their tag */
 } SeqModelParams;
 
 /* Parameters the kernels use for a zstd compression level (1..12). */

@@ -213,7 +213,15 @@ __device__ __forceinline__ uint32_t key_hash(uint32_t lo, uint32_t hi, uint32_t 
 
 // In two halves: MATCH.ANY takes a long time to come back, so a task starts the hash of its group early
 // (hash_begin) and writes the ring words when its own work is done (hash_finish).
-struct HashState { uint32_t v, m; };
+struct HashState { uint32_t v, m, tag; };
+
+// Tag stored with every table entry (15 bits).  Levels 1-4: further bits of the key hash (the key covers 5 or 6 bytes).
+// Levels 5-12 (4-byte keys): a hash of the NEXT four bytes, so that a deep scan measures only candidates that agree on
+// eight bytes; the kNearUnfiltered nearest entries are measured whatever their tag (short matches pay only nearby).
+__device__ __forceinline__ uint32_t entry_tag(bool next4, uint32_t v, uint32_t hi)
+{
+    return next4 ? (hi * 0xC2B2AE3Du) >> 17 : (v >> 4) & 0x7FFFu;
+}
 
 __device__ __forceinline__ HashState hash_begin(const Shared &S, uint32_t w, uint32_t group, uint32_t lane, uint32_t nh, uint32_t keyMask)
 {
@@ -221,7 +229,9 @@ __device__ __forceinline__ HashState hash_begin(const Shared &S, uint32_t w, uin
     const uint32_t a = S.in + (min(p, kBlockMax) & ~3u), sh = (p & 3u) * 8u;       // reads stay inside the padded buffer
     const uint32_t w0 = ldsc32(a), w1 = ldsc32(a + 4u), w2 = ldsc32(a + 8u);
     HashState h;
-    h.v = key_hash(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), keyMask);
+    const uint32_t hi = __funnelshift_r(w1, w2, sh);
+    h.v = key_hash(__funnelshift_r(w0, w1, sh), hi, keyMask);
+    h.tag = entry_tag(keyMask == 0u, h.v, hi);          // keyMask 0 <=> 4-byte keys <=> levels 5-12
     // lanes of the group in the same bucket (invalid lanes get unique keys so they never pair up)
     h.m = __match_any_sync(0xFFFFFFFFu, p < nh ? h.v >> (32 - kBucketBits) : (0x10000u | lane));
     return h;
@@ -239,7 +249,7 @@ __device__ __forceinline__ void hash_finish(const Shared &S, uint32_t w, uint32_
                           (__popc(h.m) << 23) | (first == lane ? 1u << 29 : 0u);
     const uint32_t rb = ring_byte(group, lane);
     sts32(S.ringH + (w & 1u) * (kWindow * 4u) + rb, p < nh ? word : 0u);
-    sts16(S.ringT + (w & 1u) * (kWindow * 2u) + (rb >> 1), (h.v >> 4) & 0x7FFFu);
+    sts16(S.ringT + (w & 1u) * (kWindow * 2u) + (rb >> 1), h.tag);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -549,6 +559,7 @@ __device__ __forceinline__ uint32_t measure_full(uint32_t in, uint32_t p, uint32
 #ifndef B200SP_COOP_MIN
 #define B200SP_COOP_MIN 128
 #endif
+constexpr uint32_t kNearUnfiltered = 16;   // levels 5-12: the nearest entries of a bucket are measured whatever their tag
 constexpr uint32_t kCoopMin = B200SP_COOP_MIN;     // positions with more bucket entries to scan than this are scanned by the whole warp
 
 template <bool kFuseHash>
@@ -584,17 +595,18 @@ __device__ __forceinline__ void stage_extend_full(const Shared &S, uint32_t w, u
     if (A >= Alast) chunk = ldg128_cg(sorted + 4 * A);
     HashState hs = {0u, 0u};
     if (kFuseHash) hs = hash_begin(S, hashWindow, group, lane, hashNh, keyMask);    // finished at the end of the task
-    const uint32_t tag = (key_hash(a0, a1, keyMask) >> 4) & 0x7FFFu;
+    const uint32_t tag = entry_tag(true, 0u, a1);
     uint32_t bestLen = 0, bestOff = 0;
     while (__any_sync(0xFFFFFFFFu, A >= Alast)) {
         uint32_t pend = 0;
         const uint4 cur = chunk;
         if (A >= Alast) {
             const uint32_t i0 = 4u * static_cast<uint32_t>(A);
-            if ((cur.x >> 17) == tag && i0 >= first) pend |= 1u;                       // i0 < s always holds
-            if ((cur.y >> 17) == tag && i0 + 1u >= first && i0 + 1u < s) pend |= 2u;
-            if ((cur.z >> 17) == tag && i0 + 2u >= first && i0 + 2u < s) pend |= 4u;
-            if ((cur.w >> 17) == tag && i0 + 3u >= first && i0 + 3u < s) pend |= 8u;
+            const uint32_t nearFrom = s - min(s, kNearUnfiltered);                     // entries from here on are measured whatever their tag
+            if (((cur.x >> 17) == tag || i0 >= nearFrom) && i0 >= first) pend |= 1u;                       // i0 < s always holds
+            if (((cur.y >> 17) == tag || i0 + 1u >= nearFrom) && i0 + 1u >= first && i0 + 1u < s) pend |= 2u;
+            if (((cur.z >> 17) == tag || i0 + 2u >= nearFrom) && i0 + 2u >= first && i0 + 2u < s) pend |= 4u;
+            if (((cur.w >> 17) == tag || i0 + 3u >= nearFrom) && i0 + 3u >= first && i0 + 3u < s) pend |= 8u;
             A--;
             if (A >= Alast) chunk = ldg128_cg(sorted + 4 * A);                          // in flight while we measure
         }
@@ -655,7 +667,7 @@ __device__ __forceinline__ void stage_extend_full(const Shared &S, uint32_t w, u
 #pragma unroll
                     for (int j = 3; j >= 0; j--) {
                         const uint32_t e = j == 3 ? c.w : j == 2 ? c.z : j == 1 ? c.y : c.x;
-                        if ((e >> 17) == tagi && i0 + j >= cFirst && i0 + j < cSi) {
+                        if (((e >> 17) == tagi || i0 + j + kNearUnfiltered >= cSi) && i0 + j >= cFirst && i0 + j < cSi) {
                             const uint32_t q = e & 0x1FFFFu;
                             const uint32_t ml = measure_full(in, pi, q, c0, c1, c2, c3, limi, lLen);
                             if (ml > lLen) { lLen = ml; lOff = pi - q; }
