@@ -591,7 +591,7 @@ static int ra_serve(QZSTD_Window *w, const unsigned char *src, size_t srcSize, i
  * thread (first window of a run) or on the state's helper thread (every further one). */
 static int ra_fill(QZSTD_Window *w, b200sp_engine *engine, const unsigned char *src, size_t srcSize, int level, uint32_t want)
 {
-    struct iovec local[QZSTD_RA_MAX], remote;
+    struct iovec local[QZSTD_RA_MAX], remote[QZSTD_RA_MAX];
     void *slots = NULL;
     ssize_t got;
     uint32_t n, i;
@@ -602,11 +602,13 @@ static int ra_fill(QZSTD_Window *w, b200sp_engine *engine, const unsigned char *
     for (i = 0; i < want; i++) {
         local[i].iov_base = (unsigned char *)slots + (size_t)i * B200SP_BLOCK_MAX;
         local[i].iov_len = srcSize;
+        /* one remote element per block: a transfer that stops at an unreadable page is cut between elements at the
+         * latest (process_vm_readv(2): partial transfers never split an element on some kernels) */
+        remote[i].iov_base = (void *)(src + (size_t)i * srcSize);
+        remote[i].iov_len = srcSize;
     }
-    remote.iov_base = (void *)src;
-    remote.iov_len = (size_t)want * srcSize;
     if (log_level() >= 3) t0 = ra_now();
-    got = process_vm_readv(getpid(), local, want, &remote, 1, 0);
+    got = process_vm_readv(getpid(), local, want, remote, want, 0);
     if (log_level() >= 3) t1 = ra_now();
     if (got < (ssize_t)srcSize) {
         if (got < 0 && src != NULL && errno != EFAULT) { g_raBroken = 1; QZSTD_LOG(1, "read-ahead disabled: process_vm_readv refused\n"); }
