@@ -6,21 +6,29 @@
  * distributes them over warp roles (hash/extension pool, one counting warp, parse and emit
  * warps) but must produce exactly this output.
  *
- *   1. candidates  every position p <= n-8 hashes keyBytes bytes into a 13-bit bucket and a 15-bit tag and is
- *                  appended to its bucket's list (a stable counting sort of the positions by bucket: the
- *                  "GPU-resident hash-chain table" - every bucket is the chain of ALL earlier positions with
- *                  that hash, most recent last).  The candidates of p are the `scan` entries before it in
- *                  its bucket whose tag equals its own, most recent first: the level-scaled search depth.
- *   2. extension   every candidate is measured in full (common prefix of src[p..] and src[cand..], up to
- *                  extCap and never past n); the longest wins, the nearer one on ties.  The fast classes
- *                  (levels 1-4) rank candidates on their first 16 bytes and extend the winner only.  Then a position
- *                  adopts its right neighbour's match when that match also holds one byte earlier
+ *   0. shortcut    a block whose repeated-key count stays at chance level is one literal run
+ *                  (/root/reference/src/qatseqprod.c:1308-1313).
+ *   1. candidates  every position p <= n-8 hashes keyBytes bytes into a 13-bit bucket and is appended to its bucket's
+ *                  list (a stable counting sort of the positions by bucket: the "GPU-resident hash-chain table" -
+ *                  every bucket is the chain of ALL earlier positions with that hash, most recent last), with a
+ *                  15-bit tag: further bits of the key hash (levels 1-4, keys of 5-6 bytes) or a hash of the NEXT
+ *                  four bytes (levels 5-12, keys of 4 bytes).  The candidates of p are the `scan` entries before it
+ *                  in its bucket whose tag equals its own, most recent first - the level-scaled search depth; at
+ *                  levels 5-12 the nearN nearest entries are candidates whatever their tag.
+ *   2. extension   levels 5-12: every candidate is measured in full (common prefix of src[p..] and src[cand..], up
+ *                  to extCap and never past n); the longest wins, the nearer one on ties.  Levels 1-4: candidates
+ *                  are ranked on their first 16 bytes, the winner competes with the 32-group's dominant offset
+ *                  (the stand-in for zstd's repeated-offset probe), only the final winner is extended, and a
+ *                  position adopts its right neighbour's match when that match also holds one byte earlier
  *                  (zstd's "catch up" by one; never across a 32-position group).
- *   3. propagation B(p) = the match, among all starting at q <= p, that reaches farthest right.
- *   4. parse       greedy left-to-right over B with lazy look-ahead; zero-literal sequences
- *                  repeating the previous offset are merged into their predecessor; the last
- *                  entry carries the trailing literals (convention of QZSTD_decLz4s,
- *                  /root/reference/src/qatseqprod.c:1037-1044, :1090).
+ *   3./4. levels 1-4   propagation B(p) = the match, among all starting at q <= p, that reaches farthest right;
+ *                  greedy left-to-right parse over B with lazy look-ahead (never across a 32-position group);
+ *                  zero-literal sequences repeating the previous offset are merged into their predecessor.
+ *   3./4. levels 5-12  rep_parse(): the serial repcode-aware lazy parse over the own matches (zstd's lazy parser in
+ *                  shape: repeated-offset probe one byte ahead, cheaper price for the repeated offset in the
+ *                  look-ahead, catch-up at take time, the other repeated offset tried right after every match).
+ *   5. the last entry carries the trailing literals (convention of QZSTD_decLz4s,
+ *      /root/reference/src/qatseqprod.c:1037-1044, :1090).
  */
 #include "seqmodel.h"
 #include <stdlib.h>
