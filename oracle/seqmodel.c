@@ -53,7 +53,7 @@ void seqmodel_params_for_level(int level, SeqModelParams *prm)
 {
     /* One parameter class per zstd strategy class; the scan width is the level-scaled
      * search depth (the reference hands the level to its engine, /root/reference/src/qatseqprod.c:1154). */
-    static const int scanOf[13] = { 0, 4, 4, 4, 8, 16, 24, 32, 32, 48, 64, 256, 768 };
+    static const int scanOf[13] = { 0, 4, 4, 4, 8, 16, 24, 32, 32, 48, 64, 384, 768 };
     if (level < 1) level = 1;
     if (level > 12) level = 12;
     prm->keyBytes = level <= 2 ? 6 : level <= 4 ? 5 : 4;

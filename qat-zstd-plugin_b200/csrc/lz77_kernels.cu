@@ -1368,7 +1368,7 @@ bool params_for_level(int level, ParseParams &p)
     // One parameter class per zstd strategy class; the scan width is the level-scaled search
     // depth (the reference hands the level to its engine, /root/reference/src/qatseqprod.c:1154, and rebuilds the
     // session when it changes, :1193-1201).  Must equal oracle/seqmodel.c:seqmodel_params_for_level.
-    static const uint32_t scanOf[13] = { 0, 4, 4, 4, 8, 16, 24, 32, 32, 48, 64, 256, 768 };
+    static const uint32_t scanOf[13] = { 0, 4, 4, 4, 8, 16, 24, 32, 32, 48, 64, 384, 768 };
     if (level < 1 || level > 12) return false;
     p.keyMask = level <= 2 ? 0xFFFFu : level <= 4 ? 0xFFu : 0u;   // 6-byte keys at levels 1-2, 5-byte keys at 3-4, 4-byte keys from greedy up
     p.rank16 = level <= 4 ? 1u : 0u;             // fast classes rank candidates on 16 bytes and extend the winner; the others measure every candidate in full and parse repcode-aware

@@ -52,7 +52,7 @@ def kinds(nbytes):
 BAR = 0.010
 
 
-@pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 9, 12])
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
 def test_ratio_per_kind_and_level(pkg, oracle, level):
     n = (6 if level <= 6 else 3) * BLOCK
     q = pkg.QatSeqProd

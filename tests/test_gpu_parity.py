@@ -31,7 +31,7 @@ def test_model_parity_zero_and_periodic(pkg, oracle, engine):
         check_against_model(pkg, oracle, engine, data)
 
 
-@pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 9, 12])
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 5, 6, 7, 9, 11, 12])
 def test_model_parity_all_level_classes(pkg, oracle, engine, level):
     data = datagen.mixed_corpus(5 * BLOCK + 4321, seed=20 + level)
     check_against_model(pkg, oracle, engine, data, level=level)
