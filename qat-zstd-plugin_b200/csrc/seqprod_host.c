@@ -861,6 +861,7 @@ size_t qatSequenceProducer(
     }
 
     /* batch of one block */
+    ra_quiesce(s);                  /* (the helper thread is idle here unless coalescing was switched on under a prefetch) */
     {
         b200sp_result one;
         if (b200sp_parse_host(s->engine, src, srcSize, (uint32_t)srcSize, compressionLevel, &one) != B200SP_OK ||
