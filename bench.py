@@ -159,7 +159,7 @@ def drop_in_tool(data, level):
     import re
     import tempfile
     tool = os.path.join(ROOT, "tools", "qzstd_benchmark")
-    if not os.path.exists(tool) or not os.path.exists(os.path.join(ROOT, "tools", "qzstd_handoff")):
+    if not all(os.path.exists(os.path.join(ROOT, "tools", t)) for t in ("qzstd_benchmark", "qzstd_handoff", "qzstd_producer_rate")):
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tools")], check=False)
     if not os.path.exists(tool):
         return {"unavailable": "tools/qzstd_benchmark not built"}
@@ -187,10 +187,24 @@ def drop_in_tool(data, level):
     # the step after the producer, multi-threaded: whole-buffer GPU sequences + ZSTD_compressSequences on
     # `threads` host threads, parts of 64 MiB pipelined against the GPU, buffers page-locked with QZSTD_registerBuffer; the WHOLE workload, compressed once
     hand = os.path.join(ROOT, "tools", "qzstd_handoff")
+    rate = os.path.join(ROOT, "tools", "qzstd_producer_rate")
     if os.path.exists(hand):
         with tempfile.NamedTemporaryFile(suffix=".bin") as f:
             f.write(data)
             f.flush()
+            # BASELINE.json's metric through the stock surface: raw input consumed by qatSequenceProducer alone (no hint, no
+            # entropy stage), N threads each walking the whole workload, against the software sequence producer the same way
+            if os.path.exists(rate):
+                pr = {"tool": f"tools/qzstd_producer_rate -l2 -L{level} (every thread: its own state, all {(len(data) + BLOCK - 1) // BLOCK} blocks in order)"}
+                for key, a in (("software_16t_MBps", ["-m0", "-t16"]), ("plugin_16t_MBps", ["-m1", "-t16"]), ("plugin_32t_MBps", ["-m1", "-t32"])):
+                    try:
+                        r = subprocess.run([rate] + a + ["-l2", f"-L{level}", f.name], capture_output=True, text=True, timeout=240)
+                        m = re.search(r": (\d+) MB/s of raw input, \d+ sequences, (PASS|FAIL)", r.stdout)
+                        pr[key] = int(m.group(1)) if m and m.group(2) == "PASS" else None
+                    except Exception as ex:
+                        pr[key] = None
+                        pr["error"] = str(ex)[:200]
+                out["producer_rate"] = pr
             try:
                 r = subprocess.run([hand, f"-t{threads}", "-l3", f"-L{level}", "-f8", "-p64", f.name], capture_output=True, text=True, timeout=240)
                 m = re.search(r"Hand-off: (\d+) -> (\d+) .*?: (\d+) MB/s .*?sequence production ([\d.]+) ms of ([\d.]+) ms\), (PASS|FAIL)", r.stdout)

@@ -326,3 +326,16 @@ def test_hand_off_tool_multi_thread(pkg, tmp_path):
     f.write_bytes(datagen.mixed_corpus(70 * BLOCK + 999, seed=98))
     r = subprocess.run([tool, "-t4", "-l2", "-L3", "-f4", "-p4", str(f)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+
+
+def test_producer_rate_tool(pkg, tmp_path):
+    """tools/qzstd_producer_rate: four threads through the stock qatSequenceProducer, every call answered (PASS)."""
+    import subprocess
+    tool = os.path.join(ROOT, "tools", "qzstd_producer_rate")
+    if not os.path.exists(tool):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tools")], check=True)
+    f = tmp_path / "in.bin"
+    f.write_bytes(datagen.mixed_corpus(90 * BLOCK + 31, seed=94))
+    for mode in ("-m1", "-m0"):
+        r = subprocess.run([tool, mode, "-t4", "-l2", "-L3", str(f)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
