@@ -195,10 +195,10 @@ def drop_in_tool(data, level):
             # BASELINE.json's metric through the stock surface: raw input consumed by qatSequenceProducer alone (no hint, no
             # entropy stage), N threads each walking the whole workload, against the software sequence producer the same way
             if os.path.exists(rate):
-                pr = {"tool": f"tools/qzstd_producer_rate -l2 -L{level} (every thread: its own state, all {(len(data) + BLOCK - 1) // BLOCK} blocks in order)"}
+                pr = {"tool": f"tools/qzstd_producer_rate -l4 -L{level} (every thread: its own state, all {(len(data) + BLOCK - 1) // BLOCK} blocks in order)"}
                 for key, a in (("software_16t_MBps", ["-m0", "-t16"]), ("plugin_16t_MBps", ["-m1", "-t16"]), ("plugin_32t_MBps", ["-m1", "-t32"])):
                     try:
-                        r = subprocess.run([rate] + a + ["-l2", f"-L{level}", f.name], capture_output=True, text=True, timeout=240)
+                        r = subprocess.run([rate] + a + ["-l4", f"-L{level}", f.name], capture_output=True, text=True, timeout=240)
                         m = re.search(r": (\d+) MB/s of raw input, \d+ sequences, (PASS|FAIL)", r.stdout)
                         pr[key] = int(m.group(1)) if m and m.group(2) == "PASS" else None
                     except Exception as ex:
