@@ -196,7 +196,7 @@ def drop_in_tool(data, level):
             # entropy stage), N threads each walking the whole workload, against the software sequence producer the same way
             if os.path.exists(rate):
                 pr = {"tool": f"tools/qzstd_producer_rate -l4 -L{level} (every thread: its own state, all {(len(data) + BLOCK - 1) // BLOCK} blocks in order)"}
-                for key, a in (("software_16t_MBps", ["-m0", "-t16"]), ("plugin_16t_MBps", ["-m1", "-t16"]), ("plugin_32t_MBps", ["-m1", "-t32"])):
+                for key, a in (("software_16t_MBps", ["-m0", "-t16"]), ("plugin_16t_MBps", ["-m1", "-t16"])):
                     try:
                         r = subprocess.run([rate] + a + ["-l4", f"-L{level}", f.name], capture_output=True, text=True, timeout=240)
                         m = re.search(r": (\d+) MB/s of raw input, \d+ sequences, (PASS|FAIL)", r.stdout)
